@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""Benchmark of the GM3D grouping + reconstruction-loss hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c1|c4|c5] [--impl native|reference]
+
+A "step" is one pass of the path over one batch of B synthetic clouds per GPU:
+Group (FPS -> kNN -> gather -> centre) -> hard-patch mask -> masked-patch select -> Chamfer-L2 forward with
+the per-patch / scalar reduction -> Chamfer backward (grad w.r.t. the prediction) -> loss statistics
+[-> one all-reduce of the statistics vector when N > 1].  Default workload: BASELINE config[1]
+(Point-MAE+GM3D pre-train shape, B=128, N=1024, G=64, k=32, M=39 masked patches).
+
+Prints ONE JSON line (see the field notes in DESIGN.md "Measurement").  `value` is device-resident
+throughput (inputs already in HBM, each step replayed as one CUDA graph over a ring of input/output buffer
+sets larger than L2); `e2e` feeds every step from pinned host memory and reads the loss back;
+`--impl reference` times the CPU oracle (reference operator semantics, all host threads) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "clouds/s FPS+kNN-group+Chamfer fwd/bwd"
+CONFIGS = {  # name: (B per GPU, N, G, k, mask_ratio, description)
+    "c1": (8, 1024, 64, 32, 0.6, "Point-MAE Group+Chamfer-L2 B=8 N=1024 G=64 k=32"),
+    "c2": (128, 1024, 64, 32, 0.6, "Point-MAE+GM3D pretrain B=128 N=1024 G=64 k=32 M=39 Chamfer-L2 fwd+bwd + hard-patch mask"),
+    "c4": (32, 2048, 128, 32, 0.6, "ScanObjectNN finetune shape B=32 N=2048 G=128 k=32 (+loss for uniformity)"),
+    "c5": (128, 8192, 512, 32, 0.6, "scaling sweep shard B=128/GPU N=8192 G=512 k=32 M=308"),
+}
+L2_BYTES = 126 * 1024 * 1024
+
+
+def synthetic_batch(B, N, G, k, M, seed):
+    """unit-ball clouds with per-cloud scale/translate; pred = gt-like patches + noise."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, N, 3))
+    x -= x.mean(axis=1, keepdims=True)
+    x /= np.linalg.norm(x, axis=-1).max(axis=1)[:, None, None]
+    x = x * rng.uniform(2 / 3, 3 / 2, (B, 1, 3)) + rng.uniform(-0.2, 0.2, (B, 1, 3))
+    loss_pred = rng.standard_normal((B, G))
+    # predicted patches: centre-normalised neighbourhood-sized blobs (radius ~ patch radius) -- the decoder's
+    # output distribution; values do not change the work done.
+    pred = rng.standard_normal((B * M, k, 3)) * 0.08
+    return x.astype(np.float32), loss_pred.astype(np.float32), pred.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_step(co, x, loss_pred, pred, G, k, len_keep, len_loss, rand_keys):
+    """The same step with the CPU oracle (reference operator semantics)."""
+    g = co.group(x, G, k)
+    mask = co.hard_mask(loss_pred, len_keep, len_loss, rand_keys).astype(bool)
+    gt = g["neighborhood"][mask]
+    P = gt.shape[0]
+    d1, d2, i1, i2 = co.chamfer_fwd(pred[:P], gt)
+    pp = co.chamfer_per_patch(d1, d2, 2)
+    gd = np.full((P, k), 1.0 / (P * k), dtype=np.float32)
+    ga, _ = co.chamfer_bwd(pred[:P], gt, i1, i2, gd, gd)
+    return float(pp.mean()), ga
+
+
+def time_cpu(cfg, budget_s: float, steps=None, warmup: int = 1):
+    """Time the oracle on a bounded sample: whole batches of `sample_B` clouds; returns clouds/s."""
+    from oracle import c_oracle as co
+    from gm3d_b200.masking import mask_lengths
+    B, N, G, k, ratio, _ = cfg
+    len_keep, len_loss = mask_lengths(G, ratio, 199, 400)
+    M = G - len_keep
+    x, lp, pred = synthetic_batch(B, N, G, k, M, 1234)
+    rk = np.random.default_rng(5).random((B, G)).astype(np.float32)
+    t0 = time.perf_counter()
+    cpu_step(co, x, lp, pred, G, k, len_keep, len_loss, rk)  # warm-up + calibration
+    one = time.perf_counter() - t0
+    sample_B = B
+    if steps is None:
+        steps = max(3, min(200, int(budget_s / max(one, 1e-4))))
+    elif one * (steps + warmup) > budget_s:  # shrink the per-step sample, keep whole clouds
+        sample_B = max(co.num_threads(), int(B * budget_s / (one * (steps + warmup))))
+        sample_B = min(B, sample_B)
+    xs, lps, preds, rks = x[:sample_B], lp[:sample_B], pred[: sample_B * M], rk[:sample_B]
+    for _ in range(warmup):
+        cpu_step(co, xs, lps, preds, G, k, len_keep, len_loss, rks)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(co, xs, lps, preds, G, k, len_keep, len_loss, rks)
+    dt = time.perf_counter() - t0
+    return {"value": sample_B * steps / dt, "unit": "clouds/s", "cores": co.num_threads(), "kind": "port",
+            "sample": f"{steps} steps x {sample_B} clouds of the {B}-cloud batch (N={N},G={G},k={k},M={M}), "
+                      f"C oracle on {co.num_threads()} host threads, {dt:.1f} s"}, dt / steps
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B, N, G, k, ratio, desc = cfg
+    base, ms = time_cpu(cfg, budget_s=150.0, steps=args.steps, warmup=max(1, min(args.warmup, 3)))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "clouds/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "B_per_gpu": B, "N": N, "G": G, "k": k},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ native arm
+def run_native(args, cfg):
+    import torch
+    import torch.distributed as dist
+
+    from gm3d_b200 import _lib
+    from gm3d_b200.pipeline import KERNELS_PER_STEP, GroupLossStep, HostStagedStep
+
+    _lib.load()  # fail loudly if the CUDA library is missing
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the gm3d_b200 path has no CPU fallback "
+                         "(use --impl reference for the CPU oracle)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, N, G, k, ratio, desc = cfg
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ring of buffer sets larger than L2 so every step reads cold inputs and writes cold outputs
+    probe = GroupLossStep(B, N, G, k, ratio, device=dev)
+    per_set = sum(t.numel() * t.element_size() for t in vars(probe).values() if isinstance(t, torch.Tensor))
+    ring = int(min(64, max(4, -(-2 * L2_BYTES // per_set))))
+    M = probe.M
+    del probe
+
+    def allreduce_stats(step):
+        if world > 1:
+            return lambda: dist.all_reduce(step.stats[:3])
+        return None
+
+    steps = []
+    for r in range(ring):
+        s = GroupLossStep(B, N, G, k, ratio, device=dev, seed=1234, rand_offset=(rank * ring + r) * B * G)
+        x, lp, pred = synthetic_batch(B, N, G, k, M, 1234 + 1000 * rank + r)
+        s.xyz.copy_(torch.from_numpy(x)); s.loss_pred.copy_(torch.from_numpy(lp)); s.pred.copy_(torch.from_numpy(pred))
+        steps.append(s)
+    collective_in_graph = world > 1
+    try:
+        for s in steps:
+            s.capture(allreduce_stats(s))
+    except Exception as e:  # NCCL not capturable here: keep the graph for the kernels, all-reduce eagerly
+        if world == 1:
+            raise
+        collective_in_graph = False
+        sys.stderr.write(f"[bench] all-reduce not captured ({e}); issuing it eagerly after each graph\n")
+        torch.cuda.synchronize()
+        for s in steps:
+            s.graph = None
+            s.capture(None)
+
+    def run_steps(n, start=0):
+        for i in range(n):
+            s = steps[(start + i) % ring]
+            s.run()
+            if world > 1 and not collective_in_graph:
+                dist.all_reduce(s.stats[:3])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    run_steps(W)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.15)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    run_steps(K, W)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    # keep the GPU busy a little longer so nvidia-smi gets samples under load for short runs
+    t_end = time.time() + 0.4
+    while time.time() < t_end:
+        run_steps(ring)
+        torch.cuda.synchronize()
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    value = world * B * K / (ms * 1e-3)
+    status = int(steps[0].status.item())
+    if status != 0:
+        raise SystemExit(f"bench.py: select kernel reported a bad mask row ({status})")
+
+    # ---- per-kernel device times (CUDA events on the launching stream, same ring => cold L2)
+    per_kernel = {}
+    if rank == 0:
+        L = steps[0].lib
+        st = torch.cuda.current_stream().cuda_stream
+        p = lambda t: t.data_ptr()  # noqa: E731
+        g = 1.0 / (steps[0].P * k)
+        launchers = {
+            "fps": lambda s: L.gm3d_fps_f32(p(s.xyz), B, N, G, p(s.fps_idx), p(s.center), None, st),
+            "knn_group": lambda s: _knn_group_only(L, s, st),
+            "chamfer_fwd": lambda s: L.gm3d_chamfer_fwd_f32(p(s.pred), p(s.neighborhood), p(s.patch_index), s.P, k, k,
+                                                            p(s.dist1), p(s.dist2), p(s.idx1), p(s.idx2), p(s.per_patch),
+                                                            None, 2, None, st),
+            "chamfer_bwd": lambda s: L.gm3d_chamfer_bwd_f32(p(s.pred), p(s.neighborhood), p(s.patch_index), p(s.idx1),
+                                                            p(s.idx2), None, None, g, g, s.P, k, k, p(s.grad_pred), None, st),
+            "hard_mask": lambda s: L.gm3d_hard_mask_f32(p(s.loss_pred), B, G, s.len_keep, s.len_loss, None, 1, 0, p(s.mask), st),
+        }
+        reps = max(ring, 64)
+        for name, fn in launchers.items():
+            for i in range(8):
+                fn(steps[i % ring])
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(reps):
+                fn(steps[i % ring])
+            b.record()
+            torch.cuda.synchronize()
+            per_kernel[name] = a.elapsed_time(b) * 1e3 / reps  # us per launch (incl. launch gaps)
+
+    # ---- end-to-end: every step fed from pinned host memory, results read back
+    e2e = None
+    hs = [HostStagedStep(B, N, G, k, ratio, device=dev, seed=1234, rand_offset=r * B * G) for r in range(2)]
+    for r, s in enumerate(hs):
+        x, lp, pred = synthetic_batch(B, N, G, k, M, 4321 + 1000 * rank + r)
+        s.h_xyz.copy_(torch.from_numpy(x)); s.h_pred.copy_(torch.from_numpy(pred)); s.h_loss_pred.copy_(torch.from_numpy(lp))
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    for s, strm in zip(hs, streams):
+        with torch.cuda.stream(strm):
+            s.capture(None)
+    torch.cuda.synchronize()
+    Ke = K
+    losses = []
+
+    def e2e_steps(n):
+        # two slots on two streams: copies of one step overlap the kernels of the other; the host reads each
+        # slot's loss (pinned h_stats) before re-using the slot
+        pending = [None, None]
+        for i in range(n):
+            j = i & 1
+            if pending[j] is not None:
+                pending[j].synchronize()
+                losses.append(float(hs[j].h_stats[0]))
+            with torch.cuda.stream(streams[j]):
+                hs[j].run()
+                ev = torch.cuda.Event()
+                ev.record()
+            if world > 1:
+                pass  # statistics all-reduce is part of the device-timed arm; e2e measures the host-fed path per rank
+            pending[j] = ev
+        for j in range(2):
+            if pending[j] is not None:
+                pending[j].synchronize()
+                losses.append(float(hs[j].h_stats[0]))
+
+    e2e_steps(W)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps(Ke)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = t.item()
+    e2e = {"value": world * B * Ke / dt, "unit": "clouds/s", "h2d_bytes_per_step": hs[0].h2d_bytes,
+           "d2h_bytes_per_step": hs[0].d2h_bytes, "ms_per_step": dt / Ke * 1e3,
+           "how": "2 graph slots on 2 streams fed from pinned host buffers; loss read back every step; wall clock"}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        fp32_peak = 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12  # TFLOP/s, non-tensor FP32
+        bpc = steps[0].bytes_per_cloud()
+        evals = {"fps": (G - 1) * N, "knn_group": G * N, "chamfer_fwd": 2 * M * k * k}
+        dom = max((n for n in per_kernel if n in bpc), key=lambda n: per_kernel[n])
+        ach = bpc[dom] * B / (per_kernel[dom] * 1e-6) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "us_per_launch": per_kernel[dom]}
+        detail = {}
+        for n, us in per_kernel.items():
+            d = {"us_per_launch": round(us, 3)}
+            if n in bpc:
+                d["hbm_gbs"] = round(bpc[n] * B / (us * 1e-6) / 1e9, 1)
+                d["hbm_frac"] = round(d["hbm_gbs"] / hbm_peak, 4)
+            if n in evals:
+                d["fp32_tflops"] = round(8 * evals[n] * B / (us * 1e-6) / 1e12, 2)
+                d["fp32_frac"] = round(d["fp32_tflops"] / fp32_peak, 4)
+            if n == "fps":
+                d["us_per_iteration"] = round(us / max(G - 1, 1), 4)
+            detail[n] = d
+        step_bytes = sum(bpc.values()) * B
+        cpu_base, _ = time_cpu(cfg, budget_s=12.0) if not args.no_cpu_baseline else ({"value": None, "unit": "clouds/s", "cores": 0, "kind": "port", "sample": "skipped"}, 0)
+        line = {"metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc, "B_per_gpu": B, "N": N, "G": G, "k": k, "M": M,
+                           "l2_policy": f"inputs larger than L2: ring of {ring} buffer sets x {per_set / 1e6:.1f} MB",
+                           "cuda_graph": True, "collective": ("in-graph" if collective_in_graph else "eager") if world > 1 else "none"},
+                "clocks": clk, "e2e": e2e, "gpu_launches": KERNELS_PER_STEP * K,
+                "roofline": roofline, "roofline_detail": detail,
+                "step_hbm": {"algorithmic_bytes_per_step": step_bytes,
+                             "gbs": step_bytes / (ms / K * 1e-3) / 1e9, "frac": step_bytes / (ms / K * 1e-3) / 1e9 / hbm_peak},
+                "cpu_baseline": cpu_base, "loss_check": losses[-1] if losses else None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _knn_group_only(L, s, st):
+    """The kNN + gather + normalise kernel in its Group configuration (neighbourhood written, no int64 idx)."""
+    return L.gm3d_knn_group_f32(s.xyz.data_ptr(), s.center.data_ptr(), s.B, s.N, s.G, s.k, None,
+                                s.neighborhood.data_ptr(), None, st)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=40)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_native(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,87 @@
+"""ctypes binding of libgm3d_sm100.so (the C ABI in include/gm3d.h).
+
+There is no fallback: if the shared library is missing or does not export the ABI the import of any
+operator fails with an ImportError that says how to build it (`python -m gm3d_b200.build`).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_PKG, "libgm3d_sm100.so")
+
+GM3D_ABI_VERSION = 1
+GM3D_EINVAL, GM3D_ENOSUP, GM3D_EALIGN = -1, -2, -3
+OP_FPS, OP_KNN, OP_GROUP, OP_CHAMFER_FWD, OP_CHAMFER_BWD, OP_HARD_MASK, OP_LOSS_STATS = range(1, 8)
+KNN_MAX_K = 32
+LOSS_STATS_LEN = 8
+
+_vp, _i, _u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
+
+# name -> (restype, argtypes); every symbol include/gm3d.h declares
+SIGNATURES = {
+    "gm3d_abi_version": (_i, []),
+    "gm3d_strerror": (ctypes.c_char_p, [_i]),
+    "gm3d_workspace_bytes": (ctypes.c_size_t, [_i, _i, _i, _i, _i]),
+    "gm3d_fps_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "gm3d_gather_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "gm3d_gather_grad_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "gm3d_knn_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "gm3d_knn_group_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "gm3d_group_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gm3d_chamfer_fwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "gm3d_chamfer_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _i, _i, _i, _vp, _vp, _vp]),
+    "gm3d_select_patches_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "gm3d_hard_mask_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _u64, _u64, _vp, _vp]),
+    "gm3d_loss_stats_f32": (_i, [_vp, _i, _vp, _vp]),
+}
+
+_lib = None
+
+
+class Gm3dError(RuntimeError):
+    def __init__(self, fn: str, code: int, msg: str):
+        super().__init__(f"{fn} failed: {msg} (code {code})")
+        self.code = code
+
+
+def load() -> ctypes.CDLL:
+    """Load the library once; raise ImportError (never fall back) when it is unusable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError(
+            f"{SO_PATH} is missing: the gm3d_b200 operators have no CPU or PyTorch fallback. "
+            "Build the sm_100a library with `python -m gm3d_b200.build`.")
+    try:
+        lib = ctypes.CDLL(SO_PATH)
+    except OSError as e:  # e.g. libcudart not resolvable
+        raise ImportError(f"cannot load {SO_PATH}: {e}") from e
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise ImportError(f"{SO_PATH} does not export {name}; rebuild with `python -m gm3d_b200.build --force`") from e
+        fn.restype, fn.argtypes = res, args
+    got = lib.gm3d_abi_version()
+    if got != GM3D_ABI_VERSION:
+        raise ImportError(f"{SO_PATH} has ABI version {got}, this package needs {GM3D_ABI_VERSION}; rebuild it")
+    _lib = lib
+    return lib
+
+
+def strerror(code: int) -> str:
+    return load().gm3d_strerror(code).decode()
+
+
+def check(fn: str, code: int) -> None:
+    if code == 0:
+        return
+    msg = strerror(code)
+    if code == GM3D_EINVAL:
+        raise ValueError(f"{fn}: {msg}")
+    if code == GM3D_ENOSUP:
+        raise NotImplementedError(f"{fn}: {msg}")
+    raise Gm3dError(fn, code, msg)

@@ -1,0 +1,31 @@
+// Host-only entry points of the C ABI (include/gm3d.h): version, error strings, workspace query.
+#include "common.cuh"
+
+namespace gm3d {
+size_t fps_workspace_bytes(int B, int N);
+}
+
+GM3D_API int gm3d_abi_version(void) { return GM3D_ABI_VERSION; }
+
+GM3D_API const char* gm3d_strerror(int code) {
+    switch (code) {
+        case GM3D_OK: return "success";
+        case GM3D_EINVAL: return "invalid argument (shape, k > N, G > N or a required pointer is NULL)";
+        case GM3D_ENOSUP: return "request not supported by this build (see include/gm3d.h)";
+        case GM3D_EALIGN: return "pointer is not aligned as required";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+    return "unknown gm3d error";
+}
+
+GM3D_API size_t gm3d_workspace_bytes(int op, int B, int N, int G, int k) {
+    (void)G;
+    (void)k;
+    switch (op) {
+        case GM3D_OP_FPS:
+        case GM3D_OP_GROUP: return gm3d::fps_workspace_bytes(B, N);
+        case GM3D_OP_CHAMFER_FWD: return B > 0 ? static_cast<size_t>(B) * sizeof(float) : 0;  // per-patch scratch for `total`
+        default: return 0;
+    }
+}

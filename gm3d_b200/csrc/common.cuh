@@ -1,0 +1,75 @@
+// Shared device helpers for libgm3d_sm100.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gm3d.h"
+
+#define GM3D_API extern "C" __attribute__((visibility("default")))
+
+namespace gm3d {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- FP32 distance expressions (DESIGN.md "FP32 expressions").  Intrinsics with explicit rounding are
+// never re-associated or contracted by nvcc, so the evaluation order below is what executes.
+// `a*a + b*b + c*c` as nvcc contracts it in pointnet2_ops sampling_gpu.cu and chamfer.cu:
+__device__ __forceinline__ float sumsq_nvcc(float a, float b, float c) {
+    return __fmaf_rn(c, c, __fmaf_rn(a, a, __fmul_rn(b, b)));
+}
+// KNN_CUDA cuComputeDistanceGlobal: ssd = 0; ssd += t*t over the dims (fma(a,a,0) == rn(a*a)):
+__device__ __forceinline__ float sumsq_acc(float a, float b, float c) {
+    return __fmaf_rn(c, c, __fmaf_rn(b, b, __fmul_rn(a, a)));
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// Order-preserving view of a float as a signed int for values in {-1} U [0, +inf]: non-negative floats
+// compare like their bit patterns, and any negative float maps to a negative int.
+__device__ __forceinline__ int f2ord(float f) { return __float_as_int(f); }
+
+inline int launch_status() {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? GM3D_OK : static_cast<int>(e);
+}
+
+inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+
+// ---- mbarrier + 1-D bulk copy (TMA engine; SASS: UBLKCP) ----------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; src/dst 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+}  // namespace gm3d

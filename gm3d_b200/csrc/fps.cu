@@ -1,0 +1,201 @@
+// Farthest-point sampling for sm_100a: one CTA per cloud, the cloud and its running-min array held in
+// REGISTERS (PPT points per thread), the cloud additionally staged once in shared memory (1-D bulk copy
+// through the TMA engine) so the winner's coordinates are a broadcast LDS.  One __syncthreads per round:
+// warp arg-max with two REDUX instructions (max of the order-preserving int view of the distance, then
+// min of the candidate indices), per-warp results double-buffered in shared memory, and every warp
+// re-reduces the <=32 warp results redundantly so no second barrier / broadcast is needed.
+//
+// Replaces pointnet2_utils.furthest_point_sample (+ gather_operation for the centres):
+// /root/reference/Point-MAE_SA3D/utils/miscc.py:13-20, ..._feature_besed.py:1229-1236.
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace gm3d {
+
+constexpr int kFpsMaxRegN = 8192;  // largest N served by the register-resident kernel
+
+template <int THREADS, int PPT>
+__global__ void __launch_bounds__(THREADS, 1)
+    fps_reg_kernel(const float* __restrict__ xyz, int N, int G, int32_t* __restrict__ idx,
+                   float* __restrict__ centers, int use_bulk) {
+    constexpr int NWARPS = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_xyz = reinterpret_cast<float*>(smem_raw);
+    const int n4 = (N + 3) & ~3;
+    int* s_sel = reinterpret_cast<int*>(s_xyz + 3 * n4);
+    __shared__ int2 s_red[2][32];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* cloud = xyz + static_cast<size_t>(b) * N * 3;
+
+    if (use_bulk) {
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = static_cast<uint32_t>(N) * 12u;
+            mbar_arrive_expect_tx(&s_bar, bytes);
+            bulk_g2s(s_xyz, cloud, bytes, &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
+    } else {
+        for (int i = tid; i < 3 * N; i += THREADS) s_xyz[i] = __ldg(cloud + i);
+        __syncthreads();
+    }
+
+    float px[PPT], py[PPT], pz[PPT], pt[PPT];
+#pragma unroll
+    for (int s = 0; s < PPT; ++s) {
+        const int k = s * THREADS + tid;
+        if (k < N) {
+            px[s] = s_xyz[3 * k + 0];
+            py[s] = s_xyz[3 * k + 1];
+            pz[s] = s_xyz[3 * k + 2];
+            const float mag = sumsq_nvcc(px[s], py[s], pz[s]);
+            // upstream: `if (mag <= 1e-3) continue;` with a double literal => double compare
+            pt[s] = (static_cast<double>(mag) <= 1e-3) ? -1.0f : 1e10f;
+        } else {
+            px[s] = py[s] = pz[s] = 0.0f;
+            pt[s] = -1.0f;  // min(d, -1) stays -1: never selected (ties resolve to a lower, real index)
+        }
+    }
+
+    int old = 0;
+    if (tid == 0) s_sel[0] = 0;
+    for (int j = 1; j < G; ++j) {
+        const float x1 = s_xyz[3 * old + 0], y1 = s_xyz[3 * old + 1], z1 = s_xyz[3 * old + 2];
+        float best = -1.0f;
+        int besti = 0;
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) {
+            const float d = sumsq_nvcc(px[s] - x1, py[s] - y1, pz[s] - z1);
+            const float d2 = fminf(d, pt[s]);
+            pt[s] = d2;
+            if (d2 > best) {  // strict: the lower k (= lower s) keeps a tie inside a thread
+                best = d2;
+                besti = s * THREADS + tid;
+            }
+        }
+        const int v = f2ord(best);
+        const int vmax = __reduce_max_sync(kFull, v);
+        const int kmin = __reduce_min_sync(kFull, v == vmax ? besti : INT_MAX);
+        if (NWARPS == 1) {
+            old = kmin;
+        } else {
+            if (lane == 0) s_red[j & 1][warp] = make_int2(vmax, kmin);
+            __syncthreads();
+            const int2 r = lane < NWARPS ? s_red[j & 1][lane] : make_int2(INT_MIN, INT_MAX);
+            const int gmax = __reduce_max_sync(kFull, r.x);
+            old = __reduce_min_sync(kFull, r.x == gmax ? r.y : INT_MAX);
+        }
+        if (tid == 0) s_sel[j] = old;
+    }
+    __syncthreads();
+    for (int g = tid; g < G; g += THREADS) {
+        const int i = s_sel[g];
+        idx[static_cast<size_t>(b) * G + g] = i;
+        if (centers) {
+            float* c = centers + (static_cast<size_t>(b) * G + g) * 3;
+            c[0] = s_xyz[3 * i + 0];
+            c[1] = s_xyz[3 * i + 1];
+            c[2] = s_xyz[3 * i + 2];
+        }
+    }
+}
+
+// Any N: cloud read through L1/L2, running-min array in the caller's workspace (B*N floats).
+__global__ void __launch_bounds__(1024, 1)
+    fps_global_kernel(const float* __restrict__ xyz, int N, int G, int32_t* __restrict__ idx,
+                      float* __restrict__ centers, float* __restrict__ temp_ws) {
+    __shared__ int2 s_red[2][32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* cloud = xyz + static_cast<size_t>(b) * N * 3;
+    float* temp = temp_ws + static_cast<size_t>(b) * N;
+    int32_t* out = idx + static_cast<size_t>(b) * G;
+    for (int k = tid; k < N; k += 1024) {
+        const float mag = sumsq_nvcc(cloud[3 * k], cloud[3 * k + 1], cloud[3 * k + 2]);
+        temp[k] = (static_cast<double>(mag) <= 1e-3) ? -1.0f : 1e10f;
+    }
+    int old = 0;
+    if (tid == 0) {
+        out[0] = 0;
+        if (centers) {
+            float* c = centers + static_cast<size_t>(b) * G * 3;
+            c[0] = cloud[0], c[1] = cloud[1], c[2] = cloud[2];
+        }
+    }
+    for (int j = 1; j < G; ++j) {
+        const float x1 = cloud[3 * old], y1 = cloud[3 * old + 1], z1 = cloud[3 * old + 2];
+        float best = -1.0f;
+        int besti = 0;
+        for (int k = tid; k < N; k += 1024) {
+            const float d = sumsq_nvcc(cloud[3 * k] - x1, cloud[3 * k + 1] - y1, cloud[3 * k + 2] - z1);
+            const float d2 = fminf(d, temp[k]);
+            temp[k] = d2;
+            if (d2 > best) {
+                best = d2;
+                besti = k;
+            }
+        }
+        const int v = f2ord(best);
+        const int vmax = __reduce_max_sync(kFull, v);
+        const int kmin = __reduce_min_sync(kFull, v == vmax ? besti : INT_MAX);
+        if (lane == 0) s_red[j & 1][warp] = make_int2(vmax, kmin);
+        __syncthreads();
+        const int2 r = s_red[j & 1][lane];
+        const int gmax = __reduce_max_sync(kFull, r.x);
+        old = __reduce_min_sync(kFull, r.x == gmax ? r.y : INT_MAX);
+        if (tid == 0) {
+            out[j] = old;
+            if (centers) {
+                float* c = centers + (static_cast<size_t>(b) * G + j) * 3;
+                c[0] = cloud[3 * old], c[1] = cloud[3 * old + 1], c[2] = cloud[3 * old + 2];
+            }
+        }
+    }
+}
+
+template <int THREADS, int PPT>
+static int launch_fps_reg(const float* xyz, int B, int N, int G, int32_t* idx, float* centers, cudaStream_t st) {
+    const int n4 = (N + 3) & ~3;
+    const size_t smem = static_cast<size_t>(n4) * 12 + static_cast<size_t>(G) * 4;
+    auto kern = fps_reg_kernel<THREADS, PPT>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    // bulk copy needs 16-byte aligned source rows and sizes: cloud stride 12N bytes
+    const int use_bulk = (N % 4 == 0) && (reinterpret_cast<uintptr_t>(xyz) % 16 == 0);
+    kern<<<B, THREADS, smem, st>>>(xyz, N, G, idx, centers, use_bulk);
+    return launch_status();
+}
+
+size_t fps_workspace_bytes(int B, int N) {
+    return N > kFpsMaxRegN ? static_cast<size_t>(B) * N * sizeof(float) : 0;
+}
+
+}  // namespace gm3d
+
+GM3D_API int gm3d_fps_f32(const float* xyz, int B, int N, int G, int32_t* idx, float* centers, void* ws,
+                          void* stream) {
+    using namespace gm3d;
+    if (!xyz || !idx || B <= 0 || N <= 0 || G <= 0) return GM3D_EINVAL;
+    cudaStream_t st = as_stream(stream);
+    if (N > kFpsMaxRegN) {
+        if (!ws) return GM3D_EINVAL;
+        fps_global_kernel<<<B, 1024, 0, st>>>(xyz, N, G, idx, centers, static_cast<float*>(ws));
+        return launch_status();
+    }
+    if (static_cast<size_t>((N + 3) & ~3) * 12 + static_cast<size_t>(G) * 4 > 200 * 1024) return GM3D_ENOSUP;
+    if (N <= 128) return launch_fps_reg<64, 2>(xyz, B, N, G, idx, centers, st);
+    if (N <= 256) return launch_fps_reg<128, 2>(xyz, B, N, G, idx, centers, st);
+    if (N <= 512) return launch_fps_reg<128, 4>(xyz, B, N, G, idx, centers, st);
+    if (N <= 1024) return launch_fps_reg<256, 4>(xyz, B, N, G, idx, centers, st);
+    if (N <= 2048) return launch_fps_reg<512, 4>(xyz, B, N, G, idx, centers, st);
+    if (N <= 4096) return launch_fps_reg<512, 8>(xyz, B, N, G, idx, centers, st);
+    return launch_fps_reg<1024, 8>(xyz, B, N, G, idx, centers, st);
+}

@@ -1,0 +1,87 @@
+"""Reconstruction loss glue (`forward_loss`) on top of the fused Chamfer kernels.
+
+usual mode   : /root/reference/Point-MAE_SA3D/models_mae_learn_loss_Classifier_SVM.py:968-982
+feature mode : /root/reference/Point-MAE_SA3D/models_mae_learn_loss_Classifier_SVM_feature_besed.py:976-1003
+stock scalar : /root/reference/Point-MAE_SA3D/models/Point_MAE.py:422-426
+
+`target[mask]` is never materialised: the Chamfer kernel reads the masked target patches straight out of
+the (B,G,k,3) neighbourhood tensor through a patch-index list produced by one small select kernel.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class _MaskedChamfer(torch.autograd.Function):
+    """per-point Chamfer of pred (P,n,3) against pool[patch_index] with grad w.r.t. pred only."""
+
+    @staticmethod
+    def forward(ctx, pred, pool, patch_index, norm, want):
+        d1, d2, i1, i2, pp, _ = ops.chamfer_forward(pred, pool, norm=norm, want_per_patch=True,
+                                                    xyz2_index=patch_index)
+        ctx.save_for_backward(pred, pool, patch_index, i1, i2, d1, d2)
+        ctx.want = want
+        if want == "patch":
+            return pp
+        if want == "dist1":
+            return d1
+        return d1 + d2  # 'sum'
+
+    @staticmethod
+    def backward(ctx, grad):
+        pred, pool, patch_index, i1, i2, d1, d2 = ctx.saved_tensors
+        P, n = d1.shape
+        m = d2.shape[1]
+        grad = grad.contiguous()
+        if ctx.want == "patch":
+            g1 = (grad.reshape(P, 1) / n).expand(P, n).contiguous()
+            g2 = (grad.reshape(P, 1) / m).expand(P, m).contiguous()
+        elif ctx.want == "dist1":
+            g1, g2 = grad, torch.zeros_like(d2)
+        else:
+            g1, g2 = grad, grad
+        gx1, _ = ops.chamfer_backward(pred, pool, i1, i2, g1, g2, want_grad2=False, xyz2_index=patch_index)
+        return gx1, None, None, None, None
+
+
+def masked_patch_index(mask: torch.Tensor, num_masked: int) -> torch.Tensor:
+    """(B,G) 0/1 mask (float, bool or uint8) -> (B*M,) int32 flat ids b*G+g of the masked patches, in order."""
+    if mask.dtype not in (torch.bool, torch.uint8):
+        mask = mask != 0
+    _, idx = ops.select_patches(None, mask.contiguous(), num_masked, want_out=False, want_index=True)
+    return idx
+
+
+def forward_loss_usual(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor, per_point: str = "dist1"):
+    """pred (N, M, n*3) or (N*M, n, 3); target = neighborhood (N, G, n, 3); mask (N, G) with M ones per row.
+    Returns {'MSE_mean', 'Chamfer_mean', 'matrix' (N, M)} like the reference (per_point: SURVEY F5)."""
+    N, G, n, D = target.shape
+    M = pred.numel() // (N * n * D)
+    index = masked_patch_index(mask, M)
+    pred_ = pred.reshape(-1, n, D).to(dtype=torch.float32).contiguous()
+    pool = target.reshape(N * G, n, D).to(dtype=torch.float32).contiguous()
+    loss = _MaskedChamfer.apply(pred_, pool, index, 2, per_point)
+    loss = loss.reshape(N, -1, n)
+    return {"MSE_mean": loss.mean() * 0.0, "Chamfer_mean": loss.mean(), "matrix": loss.mean(dim=-1)}
+
+
+def forward_loss_feature(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor, point_target: torch.Tensor,
+                         point_reconstructed: torch.Tensor, per_point: str = "dist1"):
+    """Feature mode: normalised-feature MSE (N, M) + per-patch Chamfer (N, M)."""
+    N, P_, D = target.shape
+    bmask = mask if mask.dtype == torch.bool else mask != 0
+    tgt = target[bmask].reshape(N, -1, D)
+    PP = tgt.shape[1]
+    pred = torch.nn.functional.normalize(pred, p=2, dim=-1)
+    tgt = torch.nn.functional.normalize(tgt, p=2, dim=-1)
+    loss_mse = ((pred - tgt) ** 2).sum(dim=-1)
+
+    n = point_target.shape[2]
+    index = masked_patch_index(bmask, PP)
+    rec = point_reconstructed.reshape(N * PP, -1, 3).to(dtype=torch.float32).contiguous()
+    pool = point_target.reshape(N * P_, n, 3).to(dtype=torch.float32).contiguous()
+    loss_chamfer = _MaskedChamfer.apply(rec, pool, index, 2, per_point)
+    loss_chamfer = loss_chamfer.reshape(N, PP, -1).mean(-1)
+    return {"MSE_mean": loss_mse.mean(), "Chamfer_mean": loss_chamfer.mean(), "matrix": loss_mse + loss_chamfer}

@@ -1,0 +1,146 @@
+"""One step of the grouping + reconstruction-loss path on preallocated buffers, captured as a CUDA graph.
+
+    xyz (B,N,3) --group--> neighborhood (B,G,k,3), center (B,G,3)
+    loss_pred (B,G) --hard mask--> mask (B,G), M ones per row --select--> patch_index (B*M)
+    pred (B*M,k,3) vs neighborhood[patch_index] --Chamfer fwd--> dist/idx, per-patch loss (B*M), scalar loss
+    --Chamfer bwd (mean reduction)--> grad_pred (B*M,k,3);   per-patch loss --stats--> (8,) vector
+    [world_size > 1: one all-reduce of the stats vector]
+
+This is the per-step sequence of the reference's pre-training loop restricted to the hot path
+(/root/reference/Point-MAE_SA3D/engine_pretrain_Classifier_SVM.py:108-118,157-184,297-305).  The step issues
+8 kernels through the C ABI; replayed as one graph it has no host work between them.  `HostStagedStep`
+adds the host<->device copies from/to pinned memory (the end-to-end arm of bench.py).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .masking import mask_lengths
+
+KERNELS_PER_STEP = 8  # fps, knn_group, hard_mask, select, chamfer_fwd, mean_reduce, chamfer_bwd, loss_stats
+
+
+class GroupLossStep:
+    def __init__(self, B: int, N: int, G: int, k: int, mask_ratio: float = 0.6, epoch: int = 199,
+                 total_epoch: int = 400, ratio_cap: float = 0.8, norm: int = 2, device=None, seed: int = 0,
+                 rand_offset: int = 0):
+        self.lib = _lib.load()
+        self.dev = torch.device(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+        if self.dev.type != "cuda":
+            raise RuntimeError("GroupLossStep runs on CUDA only (gm3d_b200 has no CPU fallback)")
+        self.B, self.N, self.G, self.k, self.norm = B, N, G, k, norm
+        self.len_keep, self.len_loss = mask_lengths(G, mask_ratio, epoch, total_epoch, True, None, ratio_cap)
+        self.M = G - self.len_keep
+        self.P = B * self.M
+        self.seed, self.rand_offset = seed, rand_offset
+        d, f32, i32 = self.dev, torch.float32, torch.int32
+        e = lambda shape, dt: torch.empty(shape, dtype=dt, device=d)  # noqa: E731
+        # inputs
+        self.xyz = e((B, N, 3), f32)
+        self.loss_pred = e((B, G), f32)
+        self.pred = e((self.P, k, 3), f32)
+        # outputs
+        self.fps_idx = e((B, G), i32)
+        self.center = e((B, G, 3), f32)
+        self.neighborhood = e((B, G, k, 3), f32)
+        self.mask = e((B, G), torch.uint8)
+        self.patch_index = e((self.P,), i32)
+        self.dist1, self.dist2 = e((self.P, k), f32), e((self.P, k), f32)
+        self.idx1, self.idx2 = e((self.P, k), i32), e((self.P, k), i32)
+        self.per_patch = e((self.P,), f32)
+        self.total = e((1,), f32)
+        self.grad_pred = e((self.P, k, 3), f32)
+        self.stats = e((_lib.LOSS_STATS_LEN,), f32)
+        self.status = torch.zeros((1,), dtype=i32, device=d)
+        ws = self.lib.gm3d_workspace_bytes(_lib.OP_GROUP, B, N, G, k)
+        self.ws = e((ws,), torch.uint8) if ws else None
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+
+    # algorithmic HBM bytes of one step per cloud (SURVEY App. B formulas; DESIGN.md "Roofline accounting")
+    def bytes_per_cloud(self):
+        N, G, k, M = self.N, self.G, self.k, self.M
+        return {
+            "fps": 12 * N + 16 * G,
+            "knn_group": 12 * N + 12 * G + 12 * G * k,           # int64 idx not requested by Group
+            "chamfer_fwd": 24 * M * k + 16 * M * k + 4 * M,
+            "chamfer_bwd": 12 * M * k * 2 + 8 * M * k + 12 * M * k,  # read both clouds + idx, write grad_pred
+            "mask_select": 5 * G + 4 * M,
+        }
+
+    def enqueue(self, stream: Optional[int] = None) -> None:
+        """Enqueue the 8 kernels of one step on `stream` (default: torch's current stream)."""
+        L, p = self.lib, (lambda t: None if t is None else t.data_ptr())
+        st = torch.cuda.current_stream(self.dev).cuda_stream if stream is None else stream
+        B, N, G, k, P = self.B, self.N, self.G, self.k, self.P
+        chk = _lib.check
+        chk("gm3d_group_f32", L.gm3d_group_f32(p(self.xyz), B, N, G, k, p(self.fps_idx), p(self.center), None,
+                                               p(self.neighborhood), None, p(self.ws), st))
+        chk("gm3d_hard_mask_f32", L.gm3d_hard_mask_f32(p(self.loss_pred), B, G, self.len_keep, self.len_loss, None,
+                                                       self.seed, self.rand_offset, p(self.mask), st))
+        chk("gm3d_select_patches_f32", L.gm3d_select_patches_f32(None, p(self.mask), B, G, k * 3, self.M, 0, None,
+                                                                 p(self.patch_index), p(self.status), st))
+        chk("gm3d_chamfer_fwd_f32", L.gm3d_chamfer_fwd_f32(p(self.pred), p(self.neighborhood), p(self.patch_index), P, k, k,
+                                                           p(self.dist1), p(self.dist2), p(self.idx1), p(self.idx2),
+                                                           p(self.per_patch), p(self.total), self.norm, None, st))
+        g = 1.0 / (P * k)  # d mean(dist1)/d dist1[p,i]
+        chk("gm3d_chamfer_bwd_f32", L.gm3d_chamfer_bwd_f32(p(self.pred), p(self.neighborhood), p(self.patch_index),
+                                                           p(self.idx1), p(self.idx2), None, None, g, g, P, k, k,
+                                                           p(self.grad_pred), None, st))
+        chk("gm3d_loss_stats_f32", L.gm3d_loss_stats_f32(p(self.per_patch), P, p(self.stats), st))
+
+    def capture(self, extra=None) -> "GroupLossStep":
+        """Capture one step (plus `extra()`, e.g. the stats all-reduce) into a CUDA graph."""
+        with torch.cuda.device(self.dev):
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):  # warm-up outside capture (cudaFuncSetAttribute, lazy module load)
+                self.enqueue()
+                if extra is not None:
+                    extra()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.enqueue()
+                if extra is not None:
+                    extra()
+            self.graph = g
+        return self
+
+    def run(self) -> None:
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.enqueue()
+
+
+class HostStagedStep(GroupLossStep):
+    """GroupLossStep fed from / drained to pinned host memory: the caller writes `h_xyz`, `h_pred`,
+    `h_loss_pred`, calls run(), and after a stream sync reads `h_stats` (loss scalars), `h_per_patch`
+    (the (B,M) loss matrix the loss predictor is trained on) and `h_mask`.  Copies are part of the graph."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # noqa: E731
+        self.h_xyz, self.h_pred, self.h_loss_pred = pin(self.xyz), pin(self.pred), pin(self.loss_pred)
+        self.h_stats, self.h_per_patch, self.h_mask = pin(self.stats), pin(self.per_patch), pin(self.mask)
+
+    @property
+    def h2d_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.h_xyz, self.h_pred, self.h_loss_pred))
+
+    @property
+    def d2h_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.h_stats, self.h_per_patch, self.h_mask))
+
+    def enqueue(self, stream: Optional[int] = None) -> None:
+        self.xyz.copy_(self.h_xyz, non_blocking=True)
+        self.pred.copy_(self.h_pred, non_blocking=True)
+        self.loss_pred.copy_(self.h_loss_pred, non_blocking=True)
+        super().enqueue(stream)
+        self.h_stats.copy_(self.stats, non_blocking=True)
+        self.h_per_patch.copy_(self.per_patch, non_blocking=True)
+        self.h_mask.copy_(self.mask, non_blocking=True)

@@ -1,0 +1,152 @@
+/*
+ * gm3d.h -- C ABI of libgm3d_sm100.so: the B200-native point-grouping + reconstruction-loss path
+ * of GeoMask3D (Point-MAE+GM3D / Point-M2AE+GM3D).
+ *
+ * Each entry point replaces one operator the reference binds from a third-party CUDA extension
+ * (paths relative to /root/reference/Point-MAE_SA3D; the extension sources themselves are not in
+ * the reference tree, so the citation is the reference's binding / call site):
+ *
+ *   gm3d_fps_f32            pointnet2_utils.furthest_point_sample   utils/miscc.py:18,
+ *                                                                   models_mae_learn_loss_Classifier_SVM_feature_besed.py:1234,
+ *                                                                   engine_finetune.py:132
+ *   gm3d_gather_f32         pointnet2_utils.gather_operation        utils/miscc.py:19, engine_finetune.py:134
+ *   gm3d_gather_grad_f32    GatherOperation.backward                (autograd of the above)
+ *   gm3d_knn_f32            knn_cuda.KNN(k, transpose_mode).forward models/Point_MAE.py:55,68
+ *   gm3d_knn_group_f32      Group.forward lines 68-77 (knn -> gather -> centre)    models/Point_MAE.py:68-77
+ *   gm3d_group_f32          Group.forward (fps -> knn -> gather -> centre)   models/Point_MAE.py:57-78,
+ *                                                                   ..._feature_besed.py:1238-1260
+ *   gm3d_chamfer_fwd_f32    chamfer.forward  (ChamferFunction)      models/Point_MAE.py:390-397,426
+ *   gm3d_chamfer_bwd_f32    chamfer.backward (ChamferFunction)      tools/runner_pretrain.py:138-151
+ *   gm3d_select_patches_f32 `neighborhood[mask].reshape(B*M,-1,3)`  models/Point_MAE.py:425,
+ *                                                                   ..._Classifier_SVM.py:972
+ *   gm3d_hard_mask_f32      generate_mask / _mask_center_rand       ..._feature_besed.py:1062-1109,
+ *                                                                   models/Point_MAE.py:297-320
+ *   gm3d_loss_stats_f32     the scalars fed to misc.all_reduce_mean util/misc.py:345-353,
+ *                                                                   engine_pretrain_Classifier_SVM.py:297-305
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer on the current CUDA device unless marked HOST.  Tensors are
+ *     dense row-major.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - Functions only ENQUEUE work: no host synchronisation, no allocation, no global state.  They are
+ *     re-entrant and may be called concurrently from several host threads on different streams.
+ *   - The caller owns inputs, outputs and workspace; the library never frees or retains a pointer.
+ *     Workspace sizes come from gm3d_workspace_bytes(); a NULL workspace is accepted when that
+ *     function returns 0 for the same arguments.
+ *   - Return value: 0 on success; > 0 is a cudaError_t from configuring / launching a kernel;
+ *     < 0 is one of the GM3D_E* codes below.  Nothing throws, nothing aborts.
+ *   - Index results are bit-exact against the CPU oracle (oracle/gm3d_oracle.c): the FP32 distance
+ *     expressions are written with explicit round-to-nearest intrinsics in the evaluation order the
+ *     upstream kernels compile to (DESIGN.md "FP32 expressions").
+ */
+#ifndef GM3D_H_
+#define GM3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GM3D_ABI_VERSION 1
+
+#define GM3D_OK 0
+#define GM3D_EINVAL (-1)  /* bad shape: B/N/G/k <= 0, k > N, G > N, NULL required pointer ...        */
+#define GM3D_ENOSUP (-2)  /* valid request this build does not cover (see each function)            */
+#define GM3D_EALIGN (-3)  /* pointer not aligned as documented                                       */
+
+#define GM3D_OP_FPS 1
+#define GM3D_OP_KNN 2
+#define GM3D_OP_GROUP 3
+#define GM3D_OP_CHAMFER_FWD 4
+#define GM3D_OP_CHAMFER_BWD 5
+#define GM3D_OP_HARD_MASK 6
+#define GM3D_OP_LOSS_STATS 7
+
+/* Largest k gm3d_knn_f32 / gm3d_group_f32 accept (one warp holds the sorted k-list, one entry per lane). */
+#define GM3D_KNN_MAX_K 32
+/* Number of floats gm3d_loss_stats_f32 writes. */
+#define GM3D_LOSS_STATS_LEN 8
+
+int gm3d_abi_version(void);
+const char* gm3d_strerror(int code); /* static storage; also decodes cudaError_t values */
+
+/* HOST-side query.  For GM3D_OP_CHAMFER_*: B = P, N = n, G = m, k ignored. */
+size_t gm3d_workspace_bytes(int op, int B, int N, int G, int k);
+
+/* Farthest-point sampling.  xyz (B,N,3) f32 -> idx (B,G) int32 [, centers (B,G,3) f32 = xyz[idx]].
+ * Starts at point 0; points with |p|^2 <= 1e-3 never update nor get selected (pointnet2_ops rule);
+ * equal running-min distances resolve to the lowest point index.  Requires 1 <= G, 1 <= N. */
+int gm3d_fps_f32(const float* xyz, int B, int N, int G, int32_t* idx, float* centers /* or NULL */, void* ws,
+                 void* stream);
+
+/* out[b,c,j] = feat[b,c,idx[b,j]].  feat (B,C,N), idx (B,G) int32, out (B,C,G). */
+int gm3d_gather_f32(const float* feat, const int32_t* idx, int B, int C, int N, int G, float* out, void* stream);
+
+/* gfeat[b,c,n] = sum_{j: idx[b,j]==n} gout[b,c,j], j ascending (deterministic, no atomics).
+ * gfeat (B,C,N) is fully written (no pre-zeroing needed). */
+int gm3d_gather_grad_f32(const float* gout, const int32_t* idx, int B, int C, int N, int G, float* gfeat,
+                         void* stream);
+
+/* Brute-force kNN.  ref (B,N,3), query (B,G,3) -> idx (B,G,k) int64 0-based, ascending by
+ * (distance, ref index); dist (B,G,k) f32 EUCLIDEAN (sqrt) or NULL.  1 <= k <= min(N, GM3D_KNN_MAX_K). */
+int gm3d_knn_f32(const float* ref, const float* query, int B, int N, int G, int k, float* dist /* or NULL */,
+                 int64_t* idx, void* ws, void* stream);
+
+/* kNN patches around GIVEN centres + gather + centre-normalisation (the second half of Group.forward,
+ * models/Point_MAE.py:68-77).  xyz (B,N,3), centers (B,G,3) -> knn_idx (B,G,k) int64 or NULL,
+ * nbhd (B,G,k,3) = xyz[knn_idx] - center, nbhd_org (B,G,k,3) or NULL. */
+int gm3d_knn_group_f32(const float* xyz, const float* centers, int B, int N, int G, int k,
+                       int64_t* knn_idx /* or NULL */, float* nbhd, float* nbhd_org /* or NULL */, void* stream);
+
+/* Fused Group.forward.  xyz (B,N,3) -> fps_idx (B,G) int32, centers (B,G,3), knn_idx (B,G,k) int64 or NULL,
+ * nbhd (B,G,k,3) = xyz[knn_idx] - center, nbhd_org (B,G,k,3) = xyz[knn_idx] or NULL. */
+int gm3d_group_f32(const float* xyz, int B, int N, int G, int k, int32_t* fps_idx, float* centers,
+                   int64_t* knn_idx /* or NULL */, float* nbhd, float* nbhd_org /* or NULL */, void* ws,
+                   void* stream);
+
+/* Chamfer forward.  xyz1 (P,n,3), xyz2 (P,m,3) -> dist1 (P,n), dist2 (P,m) squared distances,
+ * idx1 (P,n), idx2 (P,m) int32 arg-min (lowest index on ties).  Optional fused reductions:
+ *   per_patch (P): norm 2 -> mean_n dist1 + mean_m dist2;  norm 1 -> (mean_n sqrt dist1 + mean_m sqrt dist2)/2
+ *   total (1):     mean over patches of per_patch (= ChamferDistanceL2 / L1 scalar), deterministic.
+ * xyz2_index (P) int32 or NULL: when given, patch p of xyz2 is read from xyz2 + xyz2_index[p]*m*3
+ * (the masked-patch select `neighborhood[mask]` folded into the load). */
+int gm3d_chamfer_fwd_f32(const float* xyz1, const float* xyz2, const int32_t* xyz2_index /* or NULL */, int P,
+                         int n, int m, float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
+                         float* per_patch /* or NULL */, float* total /* or NULL */, int norm /* 1|2 */, void* ws,
+                         void* stream);
+
+/* Chamfer backward, atomics-free and deterministic.  With g1[p,i] = gscale1 * gdist1[p,i] (or gscale1
+ * alone when gdist1 is NULL -- the uniform upstream gradient of a mean), g2 likewise:
+ *   gxyz1[p,i] =  2 g1[p,i] (a_i - b_idx1[i]) - sum_{j: idx2[j]==i} 2 g2[p,j] (b_j - a_i)
+ *   gxyz2[p,j] =  2 g2[p,j] (b_j - a_idx2[j]) - sum_{i: idx1[i]==j} 2 g1[p,i] (a_i - b_j)
+ * gxyz2 may be NULL (target carries no gradient).  Both are fully written. */
+int gm3d_chamfer_bwd_f32(const float* xyz1, const float* xyz2, const int32_t* xyz2_index /* or NULL */,
+                         const int32_t* idx1, const int32_t* idx2, const float* gdist1 /* or NULL */,
+                         const float* gdist2 /* or NULL */, float gscale1, float gscale2, int P, int n, int m,
+                         float* gxyz1, float* gxyz2 /* or NULL */, void* stream);
+
+/* Boolean-mask patch select.  nbhd (B,G,k*3 floats per patch), mask (B,G) u8 with EXACTLY M ones per row
+ * -> out (B*M, k, 3) in row-major mask order [, patch_index (B*M) int32 = b*G+g of each selected patch].
+ * out may be NULL when only patch_index is wanted.  invert != 0 selects the zeros instead (`[~mask]`).
+ * Rows whose population count differs from M set *status (device int32, or NULL) to the row index + 1. */
+int gm3d_select_patches_f32(const float* nbhd, const uint8_t* mask, int B, int G, int row_floats, int M, int invert,
+                            float* out /* or NULL */, int32_t* patch_index /* or NULL */,
+                            int32_t* status /* or NULL */, void* stream);
+
+/* Hard-patch mask.  loss_pred (B,L) f32 -> mask (B,L) u8, 1 = masked, exactly L - len_keep ones per row:
+ * the len_loss largest loss_pred (stable order: ties -> higher index is larger) plus the
+ * (L - len_keep - len_loss) largest rand_keys among the rest.  rand_keys (B,L) f32, or NULL to draw them
+ * from Philox4x32-10(seed; counter = offset + b*L + i).  len_loss = 0 is the plain random mask. */
+int gm3d_hard_mask_f32(const float* loss_pred /* may be NULL iff len_loss == 0 */, int B, int L, int len_keep,
+                       int len_loss, const float* rand_keys /* or NULL */, uint64_t seed, uint64_t offset,
+                       uint8_t* mask, void* stream);
+
+/* Per-rank loss statistics for the one small all-reduce of a step.  per_patch (P) ->
+ * stats[GM3D_LOSS_STATS_LEN] = { sum, sum of squares, count, min, max, 0, 0, 0 } (deterministic). */
+int gm3d_loss_stats_f32(const float* per_patch, int P, float* stats, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GM3D_H_ */

@@ -1,0 +1,414 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (gm3d_b200.ops / drop-in modules), against
+the CPU oracle on identical seeded inputs and against the committed golden fixtures.
+
+Bars (BASELINE.json north_star): FPS and kNN indices bit-exact; Chamfer dist / idx exact (same FP32
+expression) and reductions / gradients within 1e-5 relative; masks exact given the same keys.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import synthetic_clouds
+from oracle import c_oracle as co
+from oracle import np_oracle as no
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # north_star: "Chamfer values and gradients within 1e-5 relative"
+
+
+def dev(a, cuda):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def test_native_library_is_loaded(cuda):
+    from gm3d_b200 import _lib
+    lib = _lib.load()
+    assert lib.gm3d_abi_version() == _lib.GM3D_ABI_VERSION
+    with open("/proc/self/maps") as f:
+        assert "libgm3d_sm100.so" in f.read()
+
+
+# ------------------------------------------------------------------------------------------ FPS
+@pytest.mark.parametrize("kind", ["ball", "sphere"])
+@pytest.mark.parametrize("B,N,G", [
+    (8, 1024, 64),     # C1
+    (4, 2048, 128),    # C4 model
+    (2, 2048, 2048),   # C4 pre-sample, G == N
+    (3, 333, 17),      # ragged: N % 4 != 0 -> non-bulk loader
+    (2, 100, 100),     # tiny, G == N
+    (2, 512, 256), (2, 256, 64),   # M2AE levels 1, 2
+    (2, 8192, 512),    # C5
+    (1, 4096, 40), (2, 127, 9), (1, 1, 1), (1, 33, 40),
+])
+def test_fps_bit_exact(cuda, kind, B, N, G):
+    from gm3d_b200 import ops
+    xyz = synthetic_clouds(B, N, 100 + N + G, kind)
+    idx, ctr = ops.fps_centers(dev(xyz, cuda), G)
+    want = co.fps(xyz, G)
+    assert idx.dtype == torch.int32 and tuple(idx.shape) == (B, G)
+    assert np.array_equal(host(idx), want)
+    assert np.array_equal(host(ctr), np.take_along_axis(xyz, want[..., None].astype(np.int64), axis=1))
+
+
+def test_fps_large_n_global_kernel(cuda):
+    from gm3d_b200 import ops
+    xyz = synthetic_clouds(2, 10000, 7, "ball")
+    idx, ctr = ops.fps_centers(dev(xyz, cuda), 50)
+    want = co.fps(xyz, 50)
+    assert np.array_equal(host(idx), want)
+    assert np.array_equal(host(ctr), np.take_along_axis(xyz, want[..., None].astype(np.int64), axis=1))
+
+
+def test_fps_skip_rule_edge(cuda):
+    from gm3d_b200 import ops
+    xyz = np.zeros((2, 16, 3), dtype=np.float32)
+    xyz[:, :, 0] = np.linspace(0.0, 0.02, 16)
+    xyz[1, 7] = [1.0, 0, 0]
+    xyz[1, 9] = [-1.0, 0, 0]
+    got = host(ops.furthest_point_sample(dev(xyz, cuda), 5))
+    assert np.array_equal(got, co.fps(xyz, 5))
+    assert (got[0] == 0).all() and got[1].tolist()[:4] == [0, 7, 9, 7]
+
+
+def test_pointnet2_dropin(cuda):
+    """furthest_point_sample + gather_operation exactly as miscc.fps calls them (utils/miscc.py:13-20)."""
+    from gm3d_b200 import pointnet2_utils
+    xyz = synthetic_clouds(4, 1024, 5, "ball")
+    data = dev(xyz, cuda)
+    fps_idx = pointnet2_utils.furthest_point_sample(data, 64)
+    assert not fps_idx.requires_grad
+    feats = data.transpose(1, 2).contiguous().requires_grad_(True)
+    out = pointnet2_utils.gather_operation(feats, fps_idx)
+    fps_data = out.transpose(1, 2).contiguous()
+    want_idx = co.fps(xyz, 64)
+    assert np.array_equal(host(fps_idx), want_idx)
+    assert np.array_equal(host(fps_data), no.fps_centers(xyz, 64))
+    assert torch.equal(fps_data, pointnet2_utils.fps(data, 64))
+    # backward = deterministic scatter-add, duplicates accumulate
+    idx = fps_idx.clone()
+    idx[:, :5] = 3
+    go = torch.randn(4, 3, 64, device=cuda)
+    pointnet2_utils.gather_operation(feats, idx).backward(go)
+    assert np.array_equal(host(feats.grad), co.gather_grad(host(go), host(idx), 1024))
+    with pytest.raises(RuntimeError):
+        pointnet2_utils.furthest_point_sample(data.cpu(), 4)
+    with pytest.raises(RuntimeError):
+        pointnet2_utils.furthest_point_sample(data.transpose(1, 2), 4)  # non-contiguous
+
+
+# ------------------------------------------------------------------------------------------ kNN
+@pytest.mark.parametrize("kind", ["ball", "sphere"])
+@pytest.mark.parametrize("B,N,G,k", [
+    (8, 1024, 64, 32), (4, 2048, 128, 32), (2, 2048, 512, 16), (2, 512, 256, 8), (2, 256, 64, 8),
+    (3, 333, 17, 5), (2, 8192, 512, 32), (2, 40, 40, 32), (1, 32, 3, 32), (2, 50, 7, 1), (1, 3000, 100, 31),
+])
+def test_knn_bit_exact(cuda, kind, B, N, G, k):
+    from gm3d_b200.knn import KNN
+    xyz = synthetic_clouds(B, N, 200 + N + k, kind)
+    rng = np.random.default_rng(N + G)
+    q = np.stack([xyz[b, rng.choice(N, G, replace=G > N)] for b in range(B)])
+    D, I = KNN(k, transpose_mode=True)(dev(xyz, cuda), dev(q, cuda))
+    Dw, Iw = co.knn(xyz, q, k)
+    assert I.dtype == torch.int64 and D.dtype == torch.float32 and tuple(I.shape) == (B, G, k)
+    assert np.array_equal(host(I), Iw)
+    assert np.array_equal(host(D).view(np.uint32), Dw.view(np.uint32))
+
+
+def test_knn_all_ties_and_transpose_mode(cuda):
+    from gm3d_b200.knn import KNN
+    ref = np.zeros((2, 200, 3), dtype=np.float32)  # every distance equal: order must be by index
+    q = np.ones((2, 5, 3), dtype=np.float32)
+    _, I = KNN(32, True)(dev(ref, cuda), dev(q, cuda))
+    assert (host(I) == np.arange(32)[None, None]).all()
+    xyz = synthetic_clouds(2, 300, 1, "ball")
+    qq = xyz[:, :11].copy()
+    D0, I0 = KNN(9, transpose_mode=False)(dev(xyz.transpose(0, 2, 1), cuda), dev(qq.transpose(0, 2, 1), cuda))
+    Dw, Iw = co.knn(xyz, qq, 9)
+    assert tuple(I0.shape) == (2, 9, 11)
+    assert np.array_equal(host(I0), Iw.transpose(0, 2, 1)) and np.array_equal(host(D0), Dw.transpose(0, 2, 1))
+    with pytest.raises(ValueError):
+        KNN(301, True)(dev(xyz, cuda), dev(qq, cuda))
+    with pytest.raises(NotImplementedError):
+        KNN(33, True)(dev(xyz, cuda), dev(qq, cuda))
+
+
+# ------------------------------------------------------------------------------------------ Group
+@pytest.mark.parametrize("tag", ["c1", "m2ae_l2", "ragged", "g_eq_n"])
+def test_group_matches_reference_golden(cuda, golden, tag):
+    """The CUDA Group against outputs of the reference's own Group.forward (tests/golden/make_golden.py)."""
+    from gm3d_b200.group import Group, GroupGM3D
+    xyz = golden[f"group_{tag}_xyz"]
+    G, k = golden[f"group_{tag}_G_k"].tolist()
+    nb, ctr = Group(G, k)(dev(xyz, cuda))
+    nb2, ctr2, org = GroupGM3D(G, k)(dev(xyz, cuda))
+    assert np.array_equal(host(ctr), golden[f"group_{tag}_center"])
+    assert np.array_equal(host(nb), golden[f"group_{tag}_neighborhood"])
+    assert np.array_equal(host(org), golden[f"group_{tag}_neighborhood_org"])
+    assert torch.equal(nb, nb2) and torch.equal(ctr, ctr2)
+    assert nb.is_contiguous() and tuple(nb.shape) == (xyz.shape[0], G, k, 3)
+    assert len(Group(G, k).state_dict()) == 0
+
+
+@pytest.mark.parametrize("B,N,G,k", [(128, 1024, 64, 32), (32, 2048, 128, 32), (16, 2048, 512, 16), (8, 8192, 512, 32)])
+def test_group_full_size_vs_oracle(cuda, B, N, G, k):
+    from gm3d_b200 import ops
+    xyz = synthetic_clouds(B, N, 1234 + N, "ball")
+    r = ops.group(dev(xyz, cuda), G, k, want_org=True, want_idx=True)
+    w = co.group(xyz, G, k)
+    assert np.array_equal(host(r["fps_idx"]), w["fps_idx"])
+    assert np.array_equal(host(r["knn_idx"]), w["knn_idx"])
+    assert np.array_equal(host(r["center"]), w["center"])
+    assert np.array_equal(host(r["neighborhood"]), w["neighborhood"])
+    assert np.array_equal(host(r["neighborhood_org"]), w["neighborhood_org"])
+
+
+def test_group_properties_at_baseline_size(cuda):
+    """Size-independent properties at the C5 shape (oracle-free): centres are cloud points, the first
+    neighbour of a centre is the centre itself (distance 0), kNN distances ascend, FPS is a prefix code
+    (the first G' picks of a G-sample equal the G'-sample)."""
+    from gm3d_b200 import ops
+    B, N, G, k = 16, 8192, 512, 32
+    xyz = dev(synthetic_clouds(B, N, 99, "ball"), cuda)
+    r = ops.group(xyz, G, k, want_org=True, want_idx=True)
+    ctr = torch.gather(xyz, 1, r["fps_idx"].long()[..., None].expand(-1, -1, 3))
+    assert torch.equal(ctr, r["center"])
+    assert torch.equal(r["neighborhood_org"][:, :, 0], r["center"])
+    assert (r["neighborhood"][:, :, 0] == 0).all()
+    gathered = torch.gather(xyz, 1, r["knn_idx"].reshape(B, -1, 1).expand(-1, -1, 3)).reshape(B, G, k, 3)
+    assert torch.equal(gathered, r["neighborhood_org"])
+    d = (r["neighborhood"].double() ** 2).sum(-1)
+    assert (d[..., 1:] >= d[..., :-1] - 1e-9).all()
+    assert torch.equal(ops.furthest_point_sample(xyz, 64), r["fps_idx"][:, :64])
+    D, I = ops.knn(xyz, r["center"], k)
+    assert torch.equal(I, r["knn_idx"])
+
+
+# ------------------------------------------------------------------------------------------ Chamfer
+@pytest.mark.parametrize("P,n,m", [(304, 32, 32), (4992, 32, 32), (1000, 16, 16), (777, 8, 8), (5, 20, 31), (3, 1, 1),
+                                   (6, 100, 70), (2, 700, 300), (3, 33, 8)])
+def test_chamfer_forward_backward(cuda, P, n, m):
+    from gm3d_b200 import ops
+    rng = np.random.default_rng(P + n)
+    a = rng.standard_normal((P, n, 3)).astype(np.float32) * 0.1
+    b = (a + 0.02 * rng.standard_normal((P, n, 3))).astype(np.float32) if n == m else \
+        rng.standard_normal((P, m, 3)).astype(np.float32) * 0.1
+    for norm in (2, 1):
+        d1, d2, i1, i2, pp, tot = ops.chamfer_forward(dev(a, cuda), dev(b, cuda), norm=norm, want_per_patch=True,
+                                                      want_total=True)
+        w1, w2, wi1, wi2 = co.chamfer_fwd(a, b)
+        assert np.array_equal(host(d1).view(np.uint32), w1.view(np.uint32))
+        assert np.array_equal(host(d2).view(np.uint32), w2.view(np.uint32))
+        assert np.array_equal(host(i1), wi1) and np.array_equal(host(i2), wi2)
+        wpp = co.chamfer_per_patch(w1, w2, norm)
+        assert np.allclose(host(pp), wpp, rtol=RTOL, atol=0)
+        assert np.isclose(host(tot)[0], wpp.mean(), rtol=RTOL, atol=0)
+    g1 = rng.standard_normal((P, n)).astype(np.float32)
+    g2 = rng.standard_normal((P, m)).astype(np.float32)
+    ga, gb = ops.chamfer_backward(dev(a, cuda), dev(b, cuda), i1, i2, dev(g1, cuda), dev(g2, cuda))
+    wa, wb = co.chamfer_bwd(a, b, wi1, wi2, g1, g2)
+    # same summation order as the C oracle -> bit-exact; and within RTOL of the float64 gradient
+    assert np.array_equal(host(ga), wa) and np.array_equal(host(gb), wb)
+    ta, tb = no.chamfer_bwd(a, b, wi1, wi2, g1, g2)
+    scale = max(np.abs(ta).max(), np.abs(tb).max())
+    assert np.abs(host(ga) - ta).max() <= RTOL * scale and np.abs(host(gb) - tb).max() <= RTOL * scale
+    ga_only, none = ops.chamfer_backward(dev(a, cuda), dev(b, cuda), i1, i2, dev(g1, cuda), dev(g2, cuda), want_grad2=False)
+    assert none is None and torch.equal(ga_only, ga)
+
+
+def test_chamfer_modules_match_stock_autograd(cuda):
+    """ChamferDistanceL2 / L1 / L2_split and their backward against a plain-PyTorch fp64 restatement."""
+    from gm3d_b200.chamfer import ChamferDistanceL1, ChamferDistanceL2, ChamferDistanceL2_split, ChamferFunction
+    torch.manual_seed(0)
+    P, n = 304, 32
+    gt = torch.randn(P, n, 3, device=cuda) * 0.1
+    pred = (gt + 0.02 * torch.randn(P, n, 3, device=cuda)).requires_grad_(True)
+
+    def ref(pred64, gt64, l1):
+        d = ((pred64[:, :, None] - gt64[:, None]) ** 2).sum(-1)
+        d1, d2 = d.min(2).values, d.min(1).values
+        return (d1.sqrt().mean() + d2.sqrt().mean()) / 2 if l1 else d1.mean() + d2.mean()
+
+    for mod, l1 in ((ChamferDistanceL2(), False), (ChamferDistanceL1(), True)):
+        pred.grad = None
+        loss = mod(pred, gt)
+        loss.backward()
+        p64 = pred.detach().double().requires_grad_(True)
+        want = ref(p64, gt.double(), l1)
+        want.backward()
+        assert loss.dim() == 0
+        assert abs(loss.item() - want.item()) <= RTOL * abs(want.item())
+        assert (pred.grad.double() - p64.grad).abs().max() <= RTOL * p64.grad.abs().max()
+    s1, s2 = ChamferDistanceL2_split()(pred, gt)
+    assert abs((s1 + s2).item() - ChamferDistanceL2()(pred, gt).item()) <= RTOL * (s1 + s2).item()
+    # reductions used by GM3D
+    d1, d2 = ChamferFunction.apply(pred, gt)
+    assert torch.allclose(ChamferDistanceL2(reduction="patch")(pred, gt), d1.mean(1) + d2.mean(1), rtol=RTOL, atol=0)
+    assert torch.equal(ChamferDistanceL2(reduction="dist1")(pred, gt), d1)
+    assert torch.equal(ChamferDistanceL2(reduction="sum")(pred, gt), d1 + d2)
+    # gradient flows to both inputs through ChamferFunction
+    gt2 = gt.clone().requires_grad_(True)
+    a, b = ChamferFunction.apply(pred, gt2)
+    (a.sum() + b.sum()).backward()
+    assert gt2.grad is not None and gt2.grad.abs().sum() > 0
+    # ignore_zeros (batch of one)
+    x1 = torch.randn(1, 40, 3, device=cuda)
+    x1[0, 5:9] = 0
+    x2 = torch.randn(1, 30, 3, device=cuda)
+    v = ChamferDistanceL2(ignore_zeros=True)(x1, x2)
+    keep = x1[0].sum(1) != 0
+    assert abs(v.item() - ChamferDistanceL2()(x1[:, keep], x2).item()) <= RTOL * abs(v.item())
+
+
+def test_chamfer_roundtrip_properties(cuda):
+    """Oracle-free properties at the C5 patch count: identical clouds -> zero distance and identity
+    arg-min; a permutation of the target only permutes idx; the scalar is symmetric in its arguments."""
+    from gm3d_b200 import ops
+    P, n = 39296, 32
+    torch.manual_seed(1)
+    a = torch.randn(P, n, 3, device=cuda)
+    d1, d2, i1, i2, pp, tot = ops.chamfer_forward(a, a.clone(), want_per_patch=True, want_total=True)
+    ar = torch.arange(n, device=cuda, dtype=torch.int32)
+    assert (d1 == 0).all() and (d2 == 0).all() and (i1 == ar).all() and (i2 == ar).all() and tot.item() == 0
+    perm = torch.randperm(n, device=cuda)
+    b = a + 0.05 * torch.randn_like(a)
+    e1, e2, j1, j2, _, t1 = ops.chamfer_forward(a, b, want_total=True)
+    f1, f2, k1, k2, _, _ = ops.chamfer_forward(a, b[:, perm].contiguous())
+    assert torch.equal(e1, f1) and torch.equal(perm[k1.long()], j1.long())
+    _, _, _, _, _, t2 = ops.chamfer_forward(b, a, want_total=True)
+    assert abs(t1.item() - t2.item()) <= RTOL * t1.item()
+
+
+# ------------------------------------------------------------------------------------------ masks / select / loss glue
+def test_hard_mask_matches_reference_golden(cuda, golden):
+    from gm3d_b200 import ops
+    lp = golden["mask_loss_pred"]
+    B, L = lp.shape
+    for key in golden["mask_cases"].tolist():
+        _, cls, e, t, a = key.split("_")
+        ref = golden[key]
+        len_keep, len_loss = no.mask_lengths(L, 0.6, int(e[1:]), int(t[1:]), True, bool(int(a[1:])) or None,
+                                             0.8 if cls == "fb" else 0.5)
+        order = np.argsort(lp, axis=1, kind="stable")
+        top = np.zeros((B, L), dtype=bool)
+        if len_loss:
+            np.put_along_axis(top, order[:, L - len_loss:], True, axis=1)
+        keys = ((ref == 1) & ~top).astype(np.float32)  # replay the reference's random picks
+        got = ops.hard_mask(dev(lp, cuda), B, L, len_keep, len_loss, rand_keys=dev(keys, cuda))
+        assert np.array_equal(host(got), ref.astype(np.uint8)), key
+
+
+def test_generate_mask_dropin(cuda):
+    from gm3d_b200 import masking
+    torch.manual_seed(3)
+    lp = torch.randn(128, 64, device=cuda)
+    for epoch in (0, 50, 199, 399):
+        m = masking.generate_mask(lp, mask_ratio=0.6, epoch=epoch, total_epoch=400)
+        assert m.dtype == torch.float32 and tuple(m.shape) == (128, 64)
+        assert (m.sum(1) == 39).all()
+        len_keep, len_loss = masking.mask_lengths(64, 0.6, epoch, 400)
+        if len_loss:
+            top = lp.argsort(dim=1)[:, -len_loss:]
+            assert (torch.gather(m, 1, top) == 1).all()
+    # philox path: reproducible from (seed, offset), different for different offsets, and uniform
+    a = masking.generate_mask(lp, 0.6, epoch=0, total_epoch=400, seed=7, offset=0)
+    b = masking.generate_mask(lp, 0.6, epoch=0, total_epoch=400, seed=7, offset=0)
+    c = masking.generate_mask(lp, 0.6, epoch=0, total_epoch=400, seed=7, offset=128 * 64)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    many = torch.stack([masking.generate_mask(lp, 0.6, epoch=0, total_epoch=400, seed=11, offset=i * 8192) for i in range(40)])
+    freq = many.mean(dim=(0, 1))
+    assert (freq - 39 / 64).abs().max() < 0.03
+    # explicit keys == oracle
+    keys = torch.rand(128, 64, device=cuda)
+    got = masking.generate_mask(lp, 0.6, epoch=199, total_epoch=400, rand_keys=keys)
+    lk, ll = masking.mask_lengths(64, 0.6, 199, 400)
+    assert np.array_equal(host(got).astype(np.uint8), co.hard_mask(host(lp), lk, ll, host(keys)))
+    rm = masking.mask_center_rand(torch.zeros(8, 64, 3, device=cuda), 0.6)
+    assert rm.dtype == torch.bool and (rm.sum(1) == 38).all()
+    assert not masking.mask_center_rand(torch.zeros(8, 64, 3, device=cuda), 0.6, noaug=True).any()
+
+
+def test_hard_mask_ties_and_sizes(cuda):
+    from gm3d_b200 import ops
+    rng = np.random.default_rng(5)
+    for L, len_keep, len_loss in [(64, 25, 15), (64, 25, 0), (64, 25, 39), (512, 205, 100), (33, 5, 7), (1, 0, 1)]:
+        lp = rng.integers(0, 5, (9, L)).astype(np.float32)
+        rk = rng.integers(0, 3, (9, L)).astype(np.float32)
+        got = ops.hard_mask(dev(lp, cuda), 9, L, len_keep, len_loss, rand_keys=dev(rk, cuda))
+        assert np.array_equal(host(got), co.hard_mask(lp, len_keep, len_loss, rk))
+    with pytest.raises(ValueError):
+        ops.hard_mask(dev(lp, cuda), 9, 1, 0, 2)
+
+
+def test_select_patches(cuda):
+    from gm3d_b200 import ops
+    rng = np.random.default_rng(6)
+    B, G, k, M = 16, 64, 32, 39
+    nb = rng.standard_normal((B, G, k, 3)).astype(np.float32)
+    mask = co.hard_mask(rng.standard_normal((B, G)).astype(np.float32), G - M, 10, rng.random((B, G)).astype(np.float32))
+    out, idx = ops.select_patches(dev(nb, cuda), dev(mask, cuda), M, want_index=True)
+    assert np.array_equal(host(out), nb[mask.astype(bool)].reshape(B * M, k, 3))
+    assert np.array_equal(host(idx), np.flatnonzero(mask.reshape(-1)))
+    vis, _ = ops.select_patches(dev(nb, cuda), dev(mask.astype(bool), cuda), G - M, invert=True)
+    assert np.array_equal(host(vis), nb[~mask.astype(bool)].reshape(B * (G - M), k, 3))
+    status = torch.zeros(1, dtype=torch.int32, device=cuda)
+    bad = mask.copy()
+    bad[3, np.flatnonzero(bad[3])[0]] = 0
+    ops.select_patches(dev(nb, cuda), dev(bad, cuda), M, status=status)
+    assert status.item() == 4  # row index + 1
+
+
+def test_forward_loss_matches_reference_golden(cuda, golden):
+    """forward_loss (usual + feature mode) against the reference's own forward_loss outputs."""
+    from gm3d_b200 import loss
+    nb, mask, pred = dev(golden["loss_neighborhood"], cuda), dev(golden["loss_mask"], cuda), dev(golden["loss_pred_points"], cuda)
+    for mode in ("dist1", "sum"):
+        p = pred.clone().requires_grad_(True)
+        r = loss.forward_loss_usual(p, nb, mask, per_point=mode)
+        assert np.allclose(host(r["matrix"]), golden[f"loss_usual_{mode}_matrix"], rtol=RTOL, atol=1e-9)
+        assert np.isclose(r["Chamfer_mean"].item(), golden[f"loss_usual_{mode}_chamfer_mean"], rtol=RTOL)
+        r["Chamfer_mean"].backward()
+        # gradient against autograd through a dense float64 restatement
+        p64 = pred.double().reshape(-1, 32, 3).requires_grad_(True)
+        gt64 = nb[mask].double().reshape(-1, 32, 3)
+        d = ((p64[:, :, None] - gt64[:, None]) ** 2).sum(-1)
+        want = d.min(2).values if mode == "dist1" else d.min(2).values + d.min(1).values
+        want.mean().backward()
+        assert (p.grad.reshape(-1, 32, 3).double() - p64.grad).abs().max() <= RTOL * p64.grad.abs().max()
+        r2 = loss.forward_loss_feature(dev(golden["loss_feature_pred"], cuda), dev(golden["loss_feature_target"], cuda),
+                                       mask, nb, pred, per_point=mode)
+        assert np.allclose(host(r2["matrix"]), golden[f"loss_feature_{mode}_matrix"], rtol=1e-4, atol=1e-6)
+        assert np.isclose(r2["Chamfer_mean"].item(), golden[f"loss_feature_{mode}_chamfer_mean"], rtol=RTOL)
+        assert np.isclose(r2["MSE_mean"].item(), golden[f"loss_feature_{mode}_mse_mean"], rtol=1e-5)
+    # stock scalar losses (models/Point_MAE.py:426)
+    from gm3d_b200.chamfer import ChamferDistanceL1, ChamferDistanceL2
+    gt = nb[mask].reshape(-1, 32, 3)
+    assert np.isclose(ChamferDistanceL2()(pred.reshape(-1, 32, 3), gt).item(), golden["cdl2_scalar"], rtol=RTOL)
+    assert np.isclose(ChamferDistanceL1()(pred.reshape(-1, 32, 3), gt).item(), golden["cdl1_scalar"], rtol=RTOL)
+
+
+def test_loss_stats(cuda):
+    from gm3d_b200 import ops
+    v = torch.rand(4992, device=cuda)
+    s = host(ops.loss_stats(v))
+    h = host(v).astype(np.float64)
+    assert np.allclose(s[:5], [h.sum(), (h * h).sum(), 4992, h.min(), h.max()], rtol=1e-6)
+
+
+def test_reference_import_lines_resolve(cuda):
+    """The reference's own import statements work unchanged after install_shims()."""
+    import gm3d_b200
+    gm3d_b200.install_shims()
+    from extensions.chamfer_dist import ChamferDistanceL1, ChamferDistanceL2  # noqa: F401  (models/Point_MAE.py:13)
+    from knn_cuda import KNN  # noqa: F401                                                  (models/Point_MAE.py:12)
+    from pointnet2_ops import pointnet2_utils  # noqa: F401                                 (utils/miscc.py:10)
+    xyz = dev(synthetic_clouds(2, 128, 1), cuda)
+    idx = pointnet2_utils.furthest_point_sample(xyz, 8)
+    ctr = pointnet2_utils.gather_operation(xyz.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+    _, I = KNN(4, transpose_mode=True)(xyz, ctr)
+    assert tuple(I.shape) == (2, 8, 4)
+    assert ChamferDistanceL2()(xyz, xyz).item() == 0
