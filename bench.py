@@ -241,39 +241,53 @@ def run_native(args, cfg):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
     value = world * B * K / (ms * 1e-3)
-    status = int(steps[0].status.item())
-    if status != 0:
-        raise SystemExit(f"bench.py: select kernel reported a bad mask row ({status})")
 
     # ---- per-kernel device times (CUDA events on the launching stream, same ring => cold L2)
     per_kernel = {}
     if rank == 0:
         L = steps[0].lib
-        st = torch.cuda.current_stream().cuda_stream
         p = lambda t: t.data_ptr()  # noqa: E731
         g = 1.0 / (steps[0].P * k)
         launchers = {
-            "fps": lambda s: L.gm3d_fps_f32(p(s.xyz), B, N, G, p(s.fps_idx), p(s.center), None, st),
-            "knn_group": lambda s: _knn_group_only(L, s, st),
-            "chamfer_fwd": lambda s: L.gm3d_chamfer_fwd_f32(p(s.pred), p(s.neighborhood), p(s.patch_index), s.P, k, k,
+            "fps": lambda s, st: L.gm3d_fps_f32(p(s.xyz), B, N, G, p(s.fps_idx), p(s.center), None, st),
+            "knn_group": lambda s, st: _knn_group_only(L, s, st),
+            "chamfer_fused": lambda s, st: L.gm3d_chamfer_fused_f32(
+                p(s.pred), p(s.neighborhood), p(s.patch_index), s.P, k, k, g, g, p(s.dist1), p(s.dist2), p(s.idx1),
+                p(s.idx2), p(s.per_patch), p(s.total), p(s.stats), 2, p(s.grad_pred), None, p(s.cd_ws), st),
+            "chamfer_fwd": lambda s, st: L.gm3d_chamfer_fwd_f32(p(s.pred), p(s.neighborhood), p(s.patch_index), s.P, k, k,
                                                             p(s.dist1), p(s.dist2), p(s.idx1), p(s.idx2), p(s.per_patch),
-                                                            None, 2, None, st),
-            "chamfer_bwd": lambda s: L.gm3d_chamfer_bwd_f32(p(s.pred), p(s.neighborhood), p(s.patch_index), p(s.idx1),
+                                                            None, None, 2, None, st),
+            "chamfer_bwd": lambda s, st: L.gm3d_chamfer_bwd_f32(p(s.pred), p(s.neighborhood), p(s.patch_index), p(s.idx1),
                                                             p(s.idx2), None, None, g, g, s.P, k, k, p(s.grad_pred), None, st),
-            "hard_mask": lambda s: L.gm3d_hard_mask_f32(p(s.loss_pred), B, G, s.len_keep, s.len_loss, None, 1, 0, p(s.mask), st),
+            "hard_mask": lambda s, st: L.gm3d_hard_mask_f32(p(s.loss_pred), B, G, s.len_keep, s.len_loss, None, 1, 0,
+                                                        p(s.mask), p(s.patch_index), st),
         }
-        reps = max(ring, 64)
         for name, fn in launchers.items():
-            for i in range(8):
-                fn(steps[i % ring])
+            # one graph holding `ring` launches of this kernel (one per buffer set => cold L2 every launch);
+            # replayed so that host launch gaps do not pollute the per-launch time
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn_st = side.cuda_stream
+                for s in steps:
+                    fn(s, fn_st)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            gk = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gk):
+                cst = torch.cuda.current_stream().cuda_stream
+                for s in steps:
+                    fn(s, cst)
+            gk.replay()
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
             a.record()
-            for i in range(reps):
-                fn(steps[i % ring])
+            for _ in range(reps):
+                gk.replay()
             b.record()
             torch.cuda.synchronize()
-            per_kernel[name] = a.elapsed_time(b) * 1e3 / reps  # us per launch (incl. launch gaps)
+            per_kernel[name] = a.elapsed_time(b) * 1e3 / (reps * ring)  # us per launch, back-to-back in a graph
 
     # ---- end-to-end: every step fed from pinned host memory, results read back
     e2e = None
@@ -334,7 +348,7 @@ def run_native(args, cfg):
         hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
         fp32_peak = 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12  # TFLOP/s, non-tensor FP32
         bpc = steps[0].bytes_per_cloud()
-        evals = {"fps": (G - 1) * N, "knn_group": G * N, "chamfer_fwd": 2 * M * k * k}
+        evals = {"fps": (G - 1) * N, "knn_group": G * N, "chamfer_fused": 2 * M * k * k, "chamfer_fwd": 2 * M * k * k}
         dom = max((n for n in per_kernel if n in bpc), key=lambda n: per_kernel[n])
         ach = bpc[dom] * B / (per_kernel[dom] * 1e-6) / 1e9
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",

@@ -30,10 +30,11 @@ SIGNATURES = {
     "gm3d_knn_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "gm3d_knn_group_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "gm3d_group_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "gm3d_chamfer_fwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "gm3d_chamfer_fwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "gm3d_chamfer_fused_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "gm3d_chamfer_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _i, _i, _i, _vp, _vp, _vp]),
     "gm3d_select_patches_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "gm3d_hard_mask_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _u64, _u64, _vp, _vp]),
+    "gm3d_hard_mask_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _u64, _u64, _vp, _vp, _vp]),
     "gm3d_loss_stats_f32": (_i, [_vp, _i, _vp, _vp]),
 }
 

@@ -3,6 +3,7 @@
 
 namespace gm3d {
 size_t fps_workspace_bytes(int B, int N);
+size_t chamfer_workspace_bytes(int P);
 }
 
 GM3D_API int gm3d_abi_version(void) { return GM3D_ABI_VERSION; }
@@ -25,7 +26,7 @@ GM3D_API size_t gm3d_workspace_bytes(int op, int B, int N, int G, int k) {
     switch (op) {
         case GM3D_OP_FPS:
         case GM3D_OP_GROUP: return gm3d::fps_workspace_bytes(B, N);
-        case GM3D_OP_CHAMFER_FWD: return B > 0 ? static_cast<size_t>(B) * sizeof(float) : 0;  // per-patch scratch for `total`
+        case GM3D_OP_CHAMFER_FWD: return gm3d::chamfer_workspace_bytes(B);  // ticket + per-patch scratch
         default: return 0;
     }
 }

@@ -1,16 +1,22 @@
 // Chamfer distance forward / backward for sm_100a.
 //
 // Patch regime (n, m <= 32 -- every GM3D / Point-MAE / Point-M2AE configuration): a sub-warp group of
-// S = 8/16/32 lanes owns one patch pair, stages both patches in shared memory with coalesced loads and
-// evaluates both directions from broadcast LDS; the per-patch L1/L2 reduction is fused (group shuffle
-// tree, fixed order).  The backward is atomics-free: lane i owns grad_xyz1[i] and walks idx2 for the
-// scatter term (and symmetrically for grad_xyz2), so the summation order is fixed and equals the CPU
-// oracle's.  General regime (any n, m): one thread per point, the other cloud streamed through shared
-// memory tiles, same arithmetic.
+// S = 8/16/32 lanes owns one patch pair.  Both patches are staged in shared memory as float4 points
+// (coalesced global loads, one LDS.128 broadcast per evaluated pair), both directions are evaluated from
+// there, and the per-patch L1/L2 reduction is fused (group shuffle tree, fixed order).  The scalar loss and
+// the loss statistics vector are produced by the LAST CTA to finish (ticket in the workspace), so the
+// whole forward -- arg-min, per-patch loss, mean, statistics -- is one launch.  `chamfer_small<S, true>`
+// additionally fuses the backward of the mean reduction (uniform upstream gradient known at launch).
+// The backward is atomics-free: lane i owns grad_xyz1[i]; the scatter term sum_{j: idx2[j]==i} is found
+// with MATCH.ANY on the arg-min targets and accumulated in ascending j, so the summation order is fixed
+// and equals the CPU oracle's.  General regime (any n, m): one thread per point, the other cloud streamed
+// through shared-memory tiles, same arithmetic.
 //
 // Replaces extensions/chamfer_dist (ChamferFunction fwd/bwd, ChamferDistanceL1/L2):
 // /root/reference/Point-MAE_SA3D/models/Point_MAE.py:390-397,426; ..._feature_besed.py:988-1003;
 // ..._Classifier_SVM.py:968-982.
+#include <float.h>
+
 #include "common.cuh"
 
 namespace gm3d {
@@ -25,18 +31,126 @@ __device__ __forceinline__ float group_sum(float v) {
     return v;
 }
 
-// ------------------------------------------------------------------------------------------------
-// forward, patch regime
-// ------------------------------------------------------------------------------------------------
+// Coalesced load of a patch of `cnt` xyz triples into float4 slots (w unused).
 template <int S>
+__device__ __forceinline__ void load_patch(float4* dst, const float* __restrict__ src, int cnt, int sub) {
+    float* d = reinterpret_cast<float*>(dst);
+    for (int t = sub; t < cnt * 3; t += S) {
+        const int pt = t / 3;
+        d[pt * 4 + (t - pt * 3)] = __ldg(src + t);
+    }
+}
+
+// Deterministic final reduction over per_patch[0..P) by one CTA: total = mean, stats = [sum, sum_sq, count,
+// min, max, mean, 0, 0].  Thread t sums elements t, t+T, ... in double, then a fixed shuffle / shared tree.
+__device__ void final_loss_reduce(const float* per_patch, int P, float* total, float* stats) {
+    __shared__ double s_sum[32], s_sq[32];
+    __shared__ float s_mn[32], s_mx[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    double sum = 0.0, sq = 0.0;
+    float mn = FLT_MAX, mx = -FLT_MAX;
+    for (int i = tid; i < P; i += blockDim.x) {
+        const float x = __ldcg(per_patch + i);  // written by other CTAs: read through L2
+        sum += x;
+        sq += static_cast<double>(x) * x;
+        mn = fminf(mn, x);
+        mx = fmaxf(mx, x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(kFull, sum, o);
+        sq += __shfl_xor_sync(kFull, sq, o);
+        mn = fminf(mn, __shfl_xor_sync(kFull, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+    }
+    if (lane == 0) s_sum[warp] = sum, s_sq[warp] = sq, s_mn[warp] = mn, s_mx[warp] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < nw; ++w) {
+            sum += s_sum[w];
+            sq += s_sq[w];
+            mn = fminf(mn, s_mn[w]);
+            mx = fmaxf(mx, s_mx[w]);
+        }
+        const float mean = static_cast<float>(sum / static_cast<double>(P));
+        if (total) total[0] = mean;
+        if (stats) {
+            stats[0] = static_cast<float>(sum);
+            stats[1] = static_cast<float>(sq);
+            stats[2] = static_cast<float>(P);
+            stats[3] = mn;
+            stats[4] = mx;
+            stats[5] = mean;
+            stats[6] = stats[7] = 0.0f;
+        }
+    }
+}
+
+// Returns true in every thread of the CTA that arrives last at `ticket` (and resets the ticket).
+__device__ __forceinline__ bool last_cta(unsigned* ticket) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+        if (s_last) *ticket = 0u;  // self-resetting: the workspace stays zeroed for the next launch
+    }
+    __syncthreads();
+    return s_last != 0;
+}
+
+// Scatter term of the backward for the lanes of one group: returns sum over source lanes l (ascending) of
+// the group with tgt[l] == my index of h[l] * (src[l] - mine), as three components SUBTRACTED from (gx,gy,gz).
+//   s_src : float4 points of the other cloud (indexed by the source lane's sub), s_h : their 2*g values,
+//   sources = bit mask (warp lane ids) of the lanes whose arg-min is this lane's point.
+template <int S>
+__device__ __forceinline__ void scatter_sub(unsigned sources, const float4* s_src, const float* s_h, float mx,
+                                            float my, float mz, float& gx, float& gy, float& gz) {
+    while (sources) {
+        const int l = __ffs(sources) - 1;
+        sources &= sources - 1;
+        const int j = l % S;
+        const float4 p = s_src[j];
+        const float h = s_h[j];
+        gx = __fsub_rn(gx, __fmul_rn(h, p.x - mx));
+        gy = __fsub_rn(gy, __fmul_rn(h, p.y - my));
+        gz = __fsub_rn(gz, __fmul_rn(h, p.z - mz));
+    }
+}
+
+// For every lane: the mask of live lanes in its group whose target (arg-min index) equals this lane's sub.
+// tgt < 0 marks a lane without a target.  s_m is a per-warp scratch of 32 words.
+template <int S>
+__device__ __forceinline__ unsigned incoming_mask(int tgt, int grp, int sub, unsigned* s_m, int lane) {
+    s_m[lane] = 0u;
+    __syncwarp();
+    const int key = tgt >= 0 ? grp * S + tgt : 1024 + lane;  // unique key for lanes without a target
+    const unsigned peers = __match_any_sync(kFull, key);
+    if (tgt >= 0) s_m[grp * S + tgt] = peers;  // every writer of a slot writes the same value
+    __syncwarp();
+    const unsigned in = s_m[grp * S + sub];
+    __syncwarp();
+    return in;
+}
+
+// ------------------------------------------------------------------------------------------------
+// patch regime: forward (+ fused reductions) and, when FUSED, the backward of the mean reduction
+// ------------------------------------------------------------------------------------------------
+template <int S, bool FUSED>
 __global__ void __launch_bounds__(kCdThreads)
-    chamfer_fwd_small(const float* __restrict__ xyz1, const float* __restrict__ xyz2,
-                      const int32_t* __restrict__ xyz2_index, int P, int n, int m, float* __restrict__ dist1,
-                      float* __restrict__ dist2, int32_t* __restrict__ idx1, int32_t* __restrict__ idx2,
-                      float* __restrict__ per_patch, int norm) {
+    chamfer_small(const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                  const int32_t* __restrict__ xyz2_index, int P, int n, int m, float* __restrict__ dist1,
+                  float* __restrict__ dist2, int32_t* __restrict__ idx1, int32_t* __restrict__ idx2,
+                  float* __restrict__ per_patch, float* __restrict__ total, float* __restrict__ stats, int norm,
+                  float gscale1, float gscale2, float* __restrict__ gxyz1, float* __restrict__ gxyz2,
+                  unsigned* __restrict__ ticket) {
     constexpr int GPW = 32 / S;  // patch pairs per warp
-    __shared__ float s_a[kCdWarps * GPW][S * 3];
-    __shared__ float s_b[kCdWarps * GPW][S * 3];
+    __shared__ float4 s_a[kCdWarps * GPW][S];
+    __shared__ float4 s_b[kCdWarps * GPW][S];
+    __shared__ float s_g1[FUSED ? kCdWarps * GPW : 1][S];
+    __shared__ float s_g2[FUSED ? kCdWarps * GPW : 1][S];
+    __shared__ unsigned s_m[FUSED ? kCdWarps : 1][32];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / S, sub = lane % S;
@@ -47,47 +161,40 @@ __global__ void __launch_bounds__(kCdThreads)
 
     const float* a = xyz1 + static_cast<size_t>(pc) * n * 3;
     const size_t bpatch = xyz2_index ? static_cast<size_t>(__ldg(xyz2_index + pc)) : static_cast<size_t>(pc);
-    const float* bsrc = xyz2 + bpatch * m * 3;
-    for (int t = sub; t < n * 3; t += S) s_a[slot][t] = __ldg(a + t);
-    for (int t = sub; t < m * 3; t += S) s_b[slot][t] = __ldg(bsrc + t);
+    load_patch<S>(s_a[slot], a, n, sub);
+    load_patch<S>(s_b[slot], xyz2 + bpatch * m * 3, m, sub);
     __syncwarp();
 
-    float f1 = 0.0f, f2 = 0.0f;
+    float f1 = 0.0f, f2 = 0.0f, best1 = 0.0f, best2 = 0.0f;
+    int besti1 = 0, besti2 = 0;
+    const float4 pa = s_a[slot][sub < n ? sub : 0], pb = s_b[slot][sub < m ? sub : 0];
     if (sub < n) {  // direction 1: a_sub against all of b (upstream: x = b - a, strict <)
-        const float ax = s_a[slot][3 * sub], ay = s_a[slot][3 * sub + 1], az = s_a[slot][3 * sub + 2];
-        float best = 0.0f;
-        int besti = 0;
-#pragma unroll 4
+#pragma unroll 8
         for (int j = 0; j < m; ++j) {
-            const float d = sumsq_nvcc(s_b[slot][3 * j] - ax, s_b[slot][3 * j + 1] - ay, s_b[slot][3 * j + 2] - az);
-            if (j == 0 || d < best) {
-                best = d;
-                besti = j;
+            const float4 q = s_b[slot][j];
+            const float d = sumsq_nvcc(q.x - pa.x, q.y - pa.y, q.z - pa.z);
+            if (j == 0 || d < best1) {
+                best1 = d;
+                besti1 = j;
             }
         }
-        if (live) {
-            dist1[static_cast<size_t>(p) * n + sub] = best;
-            idx1[static_cast<size_t>(p) * n + sub] = besti;
-        }
-        f1 = norm == 1 ? __fsqrt_rn(best) : best;
+        if (live && dist1) dist1[static_cast<size_t>(p) * n + sub] = best1;
+        if (live && idx1) idx1[static_cast<size_t>(p) * n + sub] = besti1;
+        f1 = norm == 1 ? __fsqrt_rn(best1) : best1;
     }
     if (sub < m) {  // direction 2: b_sub against all of a
-        const float bx = s_b[slot][3 * sub], by = s_b[slot][3 * sub + 1], bz = s_b[slot][3 * sub + 2];
-        float best = 0.0f;
-        int besti = 0;
-#pragma unroll 4
+#pragma unroll 8
         for (int i = 0; i < n; ++i) {
-            const float d = sumsq_nvcc(s_a[slot][3 * i] - bx, s_a[slot][3 * i + 1] - by, s_a[slot][3 * i + 2] - bz);
-            if (i == 0 || d < best) {
-                best = d;
-                besti = i;
+            const float4 q = s_a[slot][i];
+            const float d = sumsq_nvcc(q.x - pb.x, q.y - pb.y, q.z - pb.z);
+            if (i == 0 || d < best2) {
+                best2 = d;
+                besti2 = i;
             }
         }
-        if (live) {
-            dist2[static_cast<size_t>(p) * m + sub] = best;
-            idx2[static_cast<size_t>(p) * m + sub] = besti;
-        }
-        f2 = norm == 1 ? __fsqrt_rn(best) : best;
+        if (live && dist2) dist2[static_cast<size_t>(p) * m + sub] = best2;
+        if (live && idx2) idx2[static_cast<size_t>(p) * m + sub] = besti2;
+        f2 = norm == 1 ? __fsqrt_rn(best2) : best2;
     }
     if (per_patch) {
         const float s1 = group_sum<S>(f1), s2 = group_sum<S>(f2);
@@ -96,10 +203,121 @@ __global__ void __launch_bounds__(kCdThreads)
             per_patch[p] = norm == 1 ? 0.5f * v : v;
         }
     }
+
+    if (FUSED) {
+        // upstream gradient of the mean reduction: gscale (L2) or gscale * 0.5 / sqrt(d) (L1); g = 2 * that
+        const float u1 = norm == 1 ? __fmul_rn(gscale1, __fdiv_rn(0.5f, f1)) : gscale1;
+        const float u2 = norm == 1 ? __fmul_rn(gscale2, __fdiv_rn(0.5f, f2)) : gscale2;
+        const float g1 = __fmul_rn(u1, 2.0f), g2 = __fmul_rn(u2, 2.0f);
+        if (sub < n) s_g1[slot][sub] = g1;
+        if (sub < m) s_g2[slot][sub] = g2;
+        const unsigned in_a = incoming_mask<S>(sub < m ? besti2 : -1, grp, sub, s_m[warp], lane);  // j's with idx2[j]==sub
+        if (sub < n) {
+            const float4 q = s_b[slot][besti1];
+            float gx = __fmul_rn(g1, pa.x - q.x), gy = __fmul_rn(g1, pa.y - q.y), gz = __fmul_rn(g1, pa.z - q.z);
+            scatter_sub<S>(in_a, s_b[slot], s_g2[slot], pa.x, pa.y, pa.z, gx, gy, gz);
+            if (live) {
+                float* o = gxyz1 + (static_cast<size_t>(p) * n + sub) * 3;
+                o[0] = gx, o[1] = gy, o[2] = gz;
+            }
+        }
+        if (gxyz2) {
+            const unsigned in_b = incoming_mask<S>(sub < n ? besti1 : -1, grp, sub, s_m[warp], lane);
+            if (sub < m) {
+                float gx = 0.f, gy = 0.f, gz = 0.f;
+                scatter_sub<S>(in_b, s_a[slot], s_g1[slot], pb.x, pb.y, pb.z, gx, gy, gz);
+                const float4 q = s_a[slot][besti2];
+                gx = __fadd_rn(gx, __fmul_rn(g2, pb.x - q.x));
+                gy = __fadd_rn(gy, __fmul_rn(g2, pb.y - q.y));
+                gz = __fadd_rn(gz, __fmul_rn(g2, pb.z - q.z));
+                if (live) {
+                    float* o = gxyz2 + (static_cast<size_t>(p) * m + sub) * 3;
+                    o[0] = gx, o[1] = gy, o[2] = gz;
+                }
+            }
+        }
+    }
+
+    if (ticket && last_cta(ticket)) final_loss_reduce(per_patch, P, total, stats);
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward, general regime: one direction per launch. "a" = the cloud whose points own the threads.
+// patch regime: stand-alone backward (arbitrary upstream gradients, the autograd path)
+// ------------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(kCdThreads)
+    chamfer_bwd_small(const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                      const int32_t* __restrict__ xyz2_index, const int32_t* __restrict__ idx1,
+                      const int32_t* __restrict__ idx2, const float* __restrict__ gdist1,
+                      const float* __restrict__ gdist2, float gscale1, float gscale2, int P, int n, int m,
+                      float* __restrict__ gxyz1, float* __restrict__ gxyz2) {
+    constexpr int GPW = 32 / S;
+    __shared__ float4 s_a[kCdWarps * GPW][S];
+    __shared__ float4 s_b[kCdWarps * GPW][S];
+    __shared__ float s_g1[kCdWarps * GPW][S];
+    __shared__ float s_g2[kCdWarps * GPW][S];
+    __shared__ unsigned s_m[kCdWarps][32];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane / S, sub = lane % S;
+    const int slot = warp * GPW + grp;
+    const int p = (blockIdx.x * kCdWarps + warp) * GPW + grp;
+    const bool live = p < P;
+    const int pc = live ? p : 0;
+
+    const float* a = xyz1 + static_cast<size_t>(pc) * n * 3;
+    const size_t bpatch = xyz2_index ? static_cast<size_t>(__ldg(xyz2_index + pc)) : static_cast<size_t>(pc);
+    load_patch<S>(s_a[slot], a, n, sub);
+    load_patch<S>(s_b[slot], xyz2 + bpatch * m * 3, m, sub);
+    int i1 = -1, i2 = -1;
+    float g1 = 0.f, g2 = 0.f;
+    if (sub < n) {
+        const float u = gdist1 ? __fmul_rn(__ldg(gdist1 + static_cast<size_t>(pc) * n + sub), gscale1) : gscale1;
+        g1 = __fmul_rn(u, 2.0f);
+        s_g1[slot][sub] = g1;
+        i1 = __ldg(idx1 + static_cast<size_t>(pc) * n + sub);
+    }
+    if (sub < m) {
+        const float u = gdist2 ? __fmul_rn(__ldg(gdist2 + static_cast<size_t>(pc) * m + sub), gscale2) : gscale2;
+        g2 = __fmul_rn(u, 2.0f);
+        s_g2[slot][sub] = g2;
+        i2 = __ldg(idx2 + static_cast<size_t>(pc) * m + sub);
+    }
+    // clamp corrupt indices instead of reading out of bounds
+    if (i1 >= m) i1 = m - 1;
+    if (i2 >= n) i2 = n - 1;
+    __syncwarp();
+    const float4 pa = s_a[slot][sub < n ? sub : 0], pb = s_b[slot][sub < m ? sub : 0];
+
+    const unsigned in_a = incoming_mask<S>(i2, grp, sub, s_m[warp], lane);
+    if (sub < n) {
+        const float4 q = s_b[slot][i1 < 0 ? 0 : i1];
+        float gx = __fmul_rn(g1, pa.x - q.x), gy = __fmul_rn(g1, pa.y - q.y), gz = __fmul_rn(g1, pa.z - q.z);
+        scatter_sub<S>(in_a, s_b[slot], s_g2[slot], pa.x, pa.y, pa.z, gx, gy, gz);
+        if (live) {
+            float* o = gxyz1 + (static_cast<size_t>(p) * n + sub) * 3;
+            o[0] = gx, o[1] = gy, o[2] = gz;
+        }
+    }
+    if (gxyz2) {
+        const unsigned in_b = incoming_mask<S>(i1, grp, sub, s_m[warp], lane);
+        if (sub < m) {
+            float gx = 0.f, gy = 0.f, gz = 0.f;
+            scatter_sub<S>(in_b, s_a[slot], s_g1[slot], pb.x, pb.y, pb.z, gx, gy, gz);
+            const float4 q = s_a[slot][i2 < 0 ? 0 : i2];
+            gx = __fadd_rn(gx, __fmul_rn(g2, pb.x - q.x));
+            gy = __fadd_rn(gy, __fmul_rn(g2, pb.y - q.y));
+            gz = __fadd_rn(gz, __fmul_rn(g2, pb.z - q.z));
+            if (live) {
+                float* o = gxyz2 + (static_cast<size_t>(p) * m + sub) * 3;
+                o[0] = gx, o[1] = gy, o[2] = gz;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// general regime, forward: one direction per launch. "a" = the cloud whose points own the threads.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCdThreads)
     chamfer_fwd_general(const float* __restrict__ xa, const float* __restrict__ xb,
@@ -163,110 +381,15 @@ __global__ void __launch_bounds__(kCdThreads)
     }
 }
 
-// total = mean(per_patch): single CTA, fixed order (strided partials in double, shared tree).
-__global__ void __launch_bounds__(1024) mean_reduce_kernel(const float* __restrict__ v, int P, float* __restrict__ out) {
-    __shared__ double s[1024];
-    double acc = 0.0;
-    for (int i = threadIdx.x; i < P; i += 1024) acc += static_cast<double>(v[i]);
-    s[threadIdx.x] = acc;
-    __syncthreads();
-    for (int o = 512; o > 0; o >>= 1) {
-        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) out[0] = static_cast<float>(s[0] / static_cast<double>(P));
+// total / stats from per_patch: single CTA (used by the general regime and by gm3d_loss_stats_f32).
+__global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restrict__ v, int P, float* __restrict__ total,
+                                                          float* __restrict__ stats) {
+    final_loss_reduce(v, P, total, stats);
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward, patch regime
-// ------------------------------------------------------------------------------------------------
-template <int S>
-__global__ void __launch_bounds__(kCdThreads)
-    chamfer_bwd_small(const float* __restrict__ xyz1, const float* __restrict__ xyz2,
-                      const int32_t* __restrict__ xyz2_index, const int32_t* __restrict__ idx1,
-                      const int32_t* __restrict__ idx2, const float* __restrict__ gdist1,
-                      const float* __restrict__ gdist2, float gscale1, float gscale2, int P, int n, int m,
-                      float* __restrict__ gxyz1, float* __restrict__ gxyz2) {
-    constexpr int GPW = 32 / S;
-    __shared__ float s_a[kCdWarps * GPW][S * 3];
-    __shared__ float s_b[kCdWarps * GPW][S * 3];
-    __shared__ float s_g1[kCdWarps * GPW][S];
-    __shared__ float s_g2[kCdWarps * GPW][S];
-    __shared__ int s_i1[kCdWarps * GPW][S];
-    __shared__ int s_i2[kCdWarps * GPW][S];
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int grp = lane / S, sub = lane % S;
-    const int slot = warp * GPW + grp;
-    const int p = (blockIdx.x * kCdWarps + warp) * GPW + grp;
-    const bool live = p < P;
-    const int pc = live ? p : 0;
-
-    const float* a = xyz1 + static_cast<size_t>(pc) * n * 3;
-    const size_t bpatch = xyz2_index ? static_cast<size_t>(__ldg(xyz2_index + pc)) : static_cast<size_t>(pc);
-    const float* bsrc = xyz2 + bpatch * m * 3;
-    for (int t = sub; t < n * 3; t += S) s_a[slot][t] = __ldg(a + t);
-    for (int t = sub; t < m * 3; t += S) s_b[slot][t] = __ldg(bsrc + t);
-    if (sub < n) {
-        const float u = gdist1 ? __fmul_rn(__ldg(gdist1 + static_cast<size_t>(pc) * n + sub), gscale1) : gscale1;
-        s_g1[slot][sub] = __fmul_rn(u, 2.0f);
-        s_i1[slot][sub] = __ldg(idx1 + static_cast<size_t>(pc) * n + sub);
-    }
-    if (sub < m) {
-        const float u = gdist2 ? __fmul_rn(__ldg(gdist2 + static_cast<size_t>(pc) * m + sub), gscale2) : gscale2;
-        s_g2[slot][sub] = __fmul_rn(u, 2.0f);
-        s_i2[slot][sub] = __ldg(idx2 + static_cast<size_t>(pc) * m + sub);
-    }
-    __syncwarp();
-
-    if (sub < n) {  // grad wrt a_i, i = sub
-        const int i = sub;
-        const float ax = s_a[slot][3 * i], ay = s_a[slot][3 * i + 1], az = s_a[slot][3 * i + 2];
-        const int js = s_i1[slot][i];
-        const float g = s_g1[slot][i];
-        float gx = __fmul_rn(g, ax - s_b[slot][3 * js]);
-        float gy = __fmul_rn(g, ay - s_b[slot][3 * js + 1]);
-        float gz = __fmul_rn(g, az - s_b[slot][3 * js + 2]);
-        for (int j = 0; j < m; ++j) {
-            if (s_i2[slot][j] == i) {
-                const float h = s_g2[slot][j];
-                gx = __fsub_rn(gx, __fmul_rn(h, s_b[slot][3 * j] - ax));
-                gy = __fsub_rn(gy, __fmul_rn(h, s_b[slot][3 * j + 1] - ay));
-                gz = __fsub_rn(gz, __fmul_rn(h, s_b[slot][3 * j + 2] - az));
-            }
-        }
-        if (live) {
-            float* o = gxyz1 + (static_cast<size_t>(p) * n + i) * 3;
-            o[0] = gx, o[1] = gy, o[2] = gz;
-        }
-    }
-    if (gxyz2 && sub < m) {  // grad wrt b_j, j = sub
-        const int j = sub;
-        const float bx = s_b[slot][3 * j], by = s_b[slot][3 * j + 1], bz = s_b[slot][3 * j + 2];
-        float gx = 0.f, gy = 0.f, gz = 0.f;
-        for (int i = 0; i < n; ++i) {
-            if (s_i1[slot][i] == j) {
-                const float g = s_g1[slot][i];
-                gx = __fsub_rn(gx, __fmul_rn(g, s_a[slot][3 * i] - bx));
-                gy = __fsub_rn(gy, __fmul_rn(g, s_a[slot][3 * i + 1] - by));
-                gz = __fsub_rn(gz, __fmul_rn(g, s_a[slot][3 * i + 2] - bz));
-            }
-        }
-        const int is = s_i2[slot][j];
-        const float h = s_g2[slot][j];
-        gx = __fadd_rn(gx, __fmul_rn(h, bx - s_a[slot][3 * is]));
-        gy = __fadd_rn(gy, __fmul_rn(h, by - s_a[slot][3 * is + 1]));
-        gz = __fadd_rn(gz, __fmul_rn(h, bz - s_a[slot][3 * is + 2]));
-        if (live) {
-            float* o = gxyz2 + (static_cast<size_t>(p) * m + j) * 3;
-            o[0] = gx, o[1] = gy, o[2] = gz;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// backward, general regime: gradient of the cloud whose points own the threads ("a").
-//   own term:     sign_own * 2 g_a[i] (a_i - b_idx_a[i])         (added first for xyz1, last for xyz2)
+// general regime, backward: gradient of the cloud whose points own the threads ("a").
+//   own term:     2 g_a[i] (a_i - b_idx_a[i])         (added first for xyz1, last for xyz2)
 //   scatter term: - sum_{j: idx_b[j]==i} 2 g_b[j] (b_j - a_i)
 // own_first selects the oracle's accumulation order for xyz1 (own, then scatter) or xyz2 (scatter, then own).
 // ------------------------------------------------------------------------------------------------
@@ -289,7 +412,8 @@ __global__ void __launch_bounds__(kCdThreads)
     float ax = 0.f, ay = 0.f, az = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
     if (live) {
         ax = __ldg(a + 3 * i), ay = __ldg(a + 3 * i + 1), az = __ldg(a + 3 * i + 2);
-        const int js = __ldg(idx_a + static_cast<size_t>(p) * na + i);
+        int js = __ldg(idx_a + static_cast<size_t>(p) * na + i);
+        js = js < 0 ? 0 : (js >= nb ? nb - 1 : js);
         const float u = g_a ? __fmul_rn(__ldg(g_a + static_cast<size_t>(p) * na + i), gs_a) : gs_a;
         const float g = __fmul_rn(u, 2.0f);
         ox = __fmul_rn(g, ax - __ldg(bsrc + 3 * js));
@@ -325,46 +449,70 @@ __global__ void __launch_bounds__(kCdThreads)
     }
 }
 
+// Workspace layout of the forward: [0,16) ticket (must be zero on entry, left zero), [16, 16+4P) per-patch scratch.
+constexpr size_t kCdWsHeader = 16;
+
+template <bool FUSED>
+static int launch_small(const float* xyz1, const float* xyz2, const int32_t* xyz2_index, int P, int n, int m,
+                        float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, float* pp, float* total, float* stats,
+                        int norm, float g1, float g2, float* gxyz1, float* gxyz2, unsigned* ticket, cudaStream_t st) {
+    const int mx = n > m ? n : m;
+    const int S = mx <= 8 ? 8 : (mx <= 16 ? 16 : 32);
+    const int per_cta = kCdWarps * (32 / S);
+    const int grid = (P + per_cta - 1) / per_cta;
+#define GM3D_CD_LAUNCH(SS)                                                                                         \
+    chamfer_small<SS, FUSED><<<grid, kCdThreads, 0, st>>>(xyz1, xyz2, xyz2_index, P, n, m, dist1, dist2, idx1, idx2, \
+                                                          pp, total, stats, norm, g1, g2, gxyz1, gxyz2, ticket)
+    if (S == 8) GM3D_CD_LAUNCH(8);
+    else if (S == 16) GM3D_CD_LAUNCH(16);
+    else GM3D_CD_LAUNCH(32);
+#undef GM3D_CD_LAUNCH
+    return launch_status();
+}
+
+size_t chamfer_workspace_bytes(int P) { return P > 0 ? kCdWsHeader + static_cast<size_t>(P) * sizeof(float) : 0; }
+
 }  // namespace gm3d
 
 GM3D_API int gm3d_chamfer_fwd_f32(const float* xyz1, const float* xyz2, const int32_t* xyz2_index, int P, int n,
                                   int m, float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, float* per_patch,
-                                  float* total, int norm, void* ws, void* stream) {
+                                  float* total, float* stats, int norm, void* ws, void* stream) {
     using namespace gm3d;
     if (!xyz1 || !xyz2 || !dist1 || !dist2 || !idx1 || !idx2 || P <= 0 || n <= 0 || m <= 0) return GM3D_EINVAL;
     if (norm != 1 && norm != 2) return GM3D_EINVAL;
     cudaStream_t st = as_stream(stream);
+    const bool reduce = total || stats;
+    if (reduce && !ws) return GM3D_EINVAL;
     float* pp = per_patch;
-    if (total && !pp) {
-        if (!ws) return GM3D_EINVAL;
-        pp = static_cast<float*>(ws);
+    if (reduce && !pp) pp = reinterpret_cast<float*>(static_cast<char*>(ws) + kCdWsHeader);
+    if ((n > m ? n : m) <= 32) {
+        return launch_small<false>(xyz1, xyz2, xyz2_index, P, n, m, dist1, dist2, idx1, idx2, pp, total, stats, norm, 0.f,
+                                   0.f, nullptr, nullptr, reduce ? static_cast<unsigned*>(ws) : nullptr, st);
     }
-    const int mx = n > m ? n : m;
-    if (mx <= 32) {
-        const int S = mx <= 8 ? 8 : (mx <= 16 ? 16 : 32);
-        const int per_cta = kCdWarps * (32 / S);
-        const int grid = (P + per_cta - 1) / per_cta;
-        if (S == 8)
-            chamfer_fwd_small<8><<<grid, kCdThreads, 0, st>>>(xyz1, xyz2, xyz2_index, P, n, m, dist1, dist2, idx1, idx2, pp, norm);
-        else if (S == 16)
-            chamfer_fwd_small<16><<<grid, kCdThreads, 0, st>>>(xyz1, xyz2, xyz2_index, P, n, m, dist1, dist2, idx1, idx2, pp, norm);
-        else
-            chamfer_fwd_small<32><<<grid, kCdThreads, 0, st>>>(xyz1, xyz2, xyz2_index, P, n, m, dist1, dist2, idx1, idx2, pp, norm);
-    } else {
-        if (P > 65535) return GM3D_ENOSUP;
-        chamfer_fwd_general<<<dim3((n + kCdThreads - 1) / kCdThreads, P), kCdThreads, 0, st>>>(
-            xyz1, xyz2, nullptr, xyz2_index, n, m, dist1, idx1);
-        chamfer_fwd_general<<<dim3((m + kCdThreads - 1) / kCdThreads, P), kCdThreads, 0, st>>>(
-            xyz2, xyz1, xyz2_index, nullptr, m, n, dist2, idx2);
-        if (pp) chamfer_patch_reduce<<<(P + kCdWarps - 1) / kCdWarps, kCdThreads, 0, st>>>(dist1, dist2, P, n, m, norm, pp);
-    }
-    int rc = launch_status();
-    if (rc != GM3D_OK) return rc;
-    if (total) {
-        mean_reduce_kernel<<<1, 1024, 0, st>>>(pp, P, total);
-        rc = launch_status();
-    }
-    return rc;
+    if (P > 65535) return GM3D_ENOSUP;
+    chamfer_fwd_general<<<dim3((n + kCdThreads - 1) / kCdThreads, P), kCdThreads, 0, st>>>(xyz1, xyz2, nullptr, xyz2_index,
+                                                                                          n, m, dist1, idx1);
+    chamfer_fwd_general<<<dim3((m + kCdThreads - 1) / kCdThreads, P), kCdThreads, 0, st>>>(xyz2, xyz1, xyz2_index, nullptr,
+                                                                                          m, n, dist2, idx2);
+    if (pp) chamfer_patch_reduce<<<(P + kCdWarps - 1) / kCdWarps, kCdThreads, 0, st>>>(dist1, dist2, P, n, m, norm, pp);
+    if (reduce) loss_reduce_kernel<<<1, 256, 0, st>>>(pp, P, total, stats);
+    return launch_status();
+}
+
+GM3D_API int gm3d_chamfer_fused_f32(const float* xyz1, const float* xyz2, const int32_t* xyz2_index, int P, int n,
+                                    int m, float gscale1, float gscale2, float* dist1, float* dist2, int32_t* idx1,
+                                    int32_t* idx2, float* per_patch, float* total, float* stats, int norm, float* gxyz1,
+                                    float* gxyz2, void* ws, void* stream) {
+    using namespace gm3d;
+    if (!xyz1 || !xyz2 || !gxyz1 || P <= 0 || n <= 0 || m <= 0) return GM3D_EINVAL;
+    if (norm != 1 && norm != 2) return GM3D_EINVAL;
+    if ((n > m ? n : m) > 32) return GM3D_ENOSUP;  // the fused kernel serves the patch regime
+    const bool reduce = total || stats;
+    if (reduce && !ws) return GM3D_EINVAL;
+    float* pp = per_patch;
+    if (reduce && !pp) pp = reinterpret_cast<float*>(static_cast<char*>(ws) + kCdWsHeader);
+    return launch_small<true>(xyz1, xyz2, xyz2_index, P, n, m, dist1, dist2, idx1, idx2, pp, total, stats, norm, gscale1,
+                              gscale2, gxyz1, gxyz2, reduce ? static_cast<unsigned*>(ws) : nullptr, as_stream(stream));
 }
 
 GM3D_API int gm3d_chamfer_bwd_f32(const float* xyz1, const float* xyz2, const int32_t* xyz2_index,
@@ -393,5 +541,12 @@ GM3D_API int gm3d_chamfer_bwd_f32(const float* xyz1, const float* xyz2, const in
             chamfer_bwd_general<<<dim3((m + kCdThreads - 1) / kCdThreads, P), kCdThreads, 0, st>>>(
                 xyz2, xyz1, xyz2_index, nullptr, idx2, idx1, gdist2, gdist1, gscale2, gscale1, m, n, 0, gxyz2);
     }
+    return launch_status();
+}
+
+GM3D_API int gm3d_loss_stats_f32(const float* per_patch, int P, float* stats, void* stream) {
+    using namespace gm3d;
+    if (!per_patch || !stats || P <= 0) return GM3D_EINVAL;
+    loss_reduce_kernel<<<1, 256, 0, as_stream(stream)>>>(per_patch, P, nullptr, stats);
     return launch_status();
 }

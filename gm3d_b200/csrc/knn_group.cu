@@ -1,14 +1,19 @@
 // Brute-force kNN fused with the patch gather + centre-normalisation of Group.forward, for sm_100a.
 //
 // One warp owns Q queries of one cloud; a CTA of 8 warps streams the cloud through shared memory in
-// double-buffered tiles filled by 1-D bulk copies (TMA engine, mbarrier completion).  Each lane evaluates
-// one point per step against the warp's Q queries.  Selection is two-level so the scan loop contains no
-// shuffles: a candidate passes when its distance is <= the query's current k-th distance, passing lanes
-// append (distance, index) to a per-query shared-memory buffer at ballot/popc offsets, and whenever 32
-// candidates have gathered the warp sorts them (bitonic network on 64-bit keys) and merges them into its
-// sorted k-list (one key per lane), which tightens the threshold.  Keys are (float bits << 32 | index):
-// distances are non-negative so unsigned order == (distance, index) order, i.e. exactly the order
-// KNN_CUDA's stable insertion sort produces.
+// double-buffered 1024-point tiles filled by 1-D bulk copies (TMA engine, mbarrier completion).
+//
+// Selection (k <= 32, the sorted k-list lives one 64-bit key per lane; key = float bits << 32 | index, so
+// unsigned order == (distance, index) order == the order KNN_CUDA's stable insertion sort produces):
+//   * tile 0, "bootstrap": each lane evaluates its 32 points of the tile into REGISTERS and tracks its two
+//     smallest distances.  The k-th smallest of those 64 per-lane minima is a valid upper bound T of the
+//     tile's k-th distance (they are distances of 64 distinct points) and a tight one (typically k+3
+//     points pass).  Points with d <= T are compacted to shared memory (warp prefix sum of per-lane
+//     counts), sorted with one bitonic network and the few extras inserted.  If more than 64 points pass
+//     (heavy ties / duplicates) the tile falls back to the streaming path below.
+//   * tiles 1.., "streaming": one point per lane per step, `d <= current k-th distance` filter, passing
+//     lanes append at ballot/popc offsets to the shared-memory buffer; every 32 gathered candidates are
+//     sorted and merged into the k-list, which tightens the filter.  No shuffles in the scan loop.
 //
 // Replaces knn_cuda.KNN(k, transpose_mode=True).forward and the index arithmetic / gather / subtract of
 // Group.forward: /root/reference/Point-MAE_SA3D/models/Point_MAE.py:57-78, ..._feature_besed.py:1238-1260.
@@ -18,43 +23,58 @@ namespace gm3d {
 
 constexpr int kKnnWarps = 8;
 constexpr int kKnnThreads = kKnnWarps * 32;
-constexpr int kKnnTile = 1024;  // points per shared-memory tile (12 KB)
+constexpr int kKnnTile = 1024;  // points per shared-memory tile (12 KB); bootstrap holds 32 per lane
+constexpr unsigned kInfBits = 0x7f800000u;
 // sentinel: distance bits of +inf, index 0xffffffff -- larger than any real candidate with a non-NaN distance
-constexpr unsigned long long kKeyInf = (0x7f800000ull << 32) | 0xffffffffull;
+constexpr unsigned long long kKeyInf = (static_cast<unsigned long long>(kInfBits) << 32) | 0xffffffffull;
 
-__device__ __forceinline__ unsigned long long umin64(unsigned long long a, unsigned long long b) {
-    return a < b ? a : b;
-}
-__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) {
-    return a < b ? b : a;
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 umin64(u64 a, u64 b) { return a < b ? a : b; }
+__device__ __forceinline__ u64 make_key(float d, unsigned idx) {
+    return (static_cast<u64>(__float_as_uint(d)) << 32) | idx;
 }
 
-// Ascending bitonic sort of one 64-bit key per lane.
-__device__ __forceinline__ unsigned long long bitonic_sort32(unsigned long long v, int lane) {
+// Ascending bitonic sort of one key per lane.
+template <typename T>
+__device__ __forceinline__ T bitonic_sort32(T v, int lane) {
 #pragma unroll
     for (int sz = 2; sz <= 32; sz <<= 1) {
 #pragma unroll
         for (int st = sz >> 1; st > 0; st >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(kFull, v, st);
+            const T o = __shfl_xor_sync(kFull, v, st);
             const bool up = (lane & sz) == 0;  // sz == 32: always ascending
             const bool lower = (lane & st) == 0;
-            v = (lower == up) ? umin64(v, o) : umax64(v, o);
+            const T lo = v < o ? v : o, hi = v < o ? o : v;
+            v = (lower == up) ? lo : hi;
         }
     }
     return v;
 }
 
-// top (ascending, one per lane) <- the 32 smallest of top U cand (cand ascending).
-__device__ __forceinline__ unsigned long long merge_sorted32(unsigned long long top, unsigned long long cand,
-                                                             int lane) {
-    const unsigned long long rev = __shfl_sync(kFull, cand, 31 - lane);
-    unsigned long long v = umin64(top, rev);  // bitonic, holds the 32 smallest of the union
+// Sort a bitonic sequence (one element per lane) ascending.
+template <typename T>
+__device__ __forceinline__ T bitonic_merge32(T v, int lane) {
 #pragma unroll
     for (int st = 16; st > 0; st >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(kFull, v, st);
-        v = (lane & st) == 0 ? umin64(v, o) : umax64(v, o);
+        const T o = __shfl_xor_sync(kFull, v, st);
+        const T lo = v < o ? v : o, hi = v < o ? o : v;
+        v = (lane & st) == 0 ? lo : hi;
     }
     return v;
+}
+
+// top (ascending, one per lane) <- the 32 smallest of top U cand (cand ascending).
+__device__ __forceinline__ u64 merge_sorted32(u64 top, u64 cand, int lane) {
+    const u64 rev = __shfl_sync(kFull, cand, 31 - lane);
+    return bitonic_merge32(umin64(top, rev), lane);  // min(...) is bitonic and holds the 32 smallest
+}
+
+// Insert one warp-uniform key into the ascending per-lane list (the largest element falls off lane 31).
+__device__ __forceinline__ u64 insert_sorted32(u64 top, u64 e, int lane) {
+    const u64 up = __shfl_up_sync(kFull, top, 1);
+    if (top > e) top = (lane > 0 && up > e) ? up : e;
+    return top;
 }
 
 template <int Q>
@@ -63,7 +83,7 @@ __global__ void __launch_bounds__(kKnnThreads)
                      float* __restrict__ dist_out, int64_t* __restrict__ idx_out, float* __restrict__ nbhd,
                      float* __restrict__ nbhd_org, int use_bulk) {
     __shared__ __align__(16) float s_tile[2][kKnnTile * 3];
-    __shared__ unsigned long long s_cand[kKnnWarps][Q][64];
+    __shared__ u64 s_cand[kKnnWarps][Q][64];
     __shared__ __align__(8) uint64_t s_full[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -98,7 +118,7 @@ __global__ void __launch_bounds__(kKnnThreads)
     if (ntiles > 1) load_tile(1);
 
     float qx[Q], qy[Q], qz[Q], thr[Q];
-    unsigned long long top[Q];
+    u64 top[Q];
     int cnt[Q];
     bool act[Q];
 #pragma unroll
@@ -108,21 +128,30 @@ __global__ void __launch_bounds__(kKnnThreads)
         qx[q] = __ldg(qp + 0);
         qy[q] = __ldg(qp + 1);
         qz[q] = __ldg(qp + 2);
-        thr[q] = __int_as_float(0x7f800000);  // +inf
+        thr[q] = __uint_as_float(kInfBits);
         top[q] = kKeyInf;
         cnt[q] = 0;
     }
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    for (int t = 0; t < ntiles; ++t) {
-        if (use_bulk) {
-            mbar_wait(&s_full[t & 1], (t >> 1) & 1);
-        } else {
-            __syncthreads();
-        }
-        const float* tile = s_tile[t & 1];
-        const int base = t * kKnnTile;
-        const int npts = min(kKnnTile, N - base);
+    // Merge the first 32 buffered candidates of query q into its k-list and tighten the filter.
+    auto flush32 = [&](int q) {
+        u64* cb = s_cand[warp][q];
+        __syncwarp();
+        u64 c = cb[lane];
+        const int rem = cnt[q] - 32;
+        const u64 r = lane < rem ? cb[32 + lane] : 0ull;
+        __syncwarp();
+        if (lane < rem) cb[lane] = r;
+        cnt[q] = rem;
+        c = bitonic_sort32(c, lane);
+        top[q] = merge_sorted32(top[q], c, lane);
+        thr[q] = __uint_as_float(static_cast<unsigned>(__shfl_sync(kFull, top[q], k - 1) >> 32));
+        __syncwarp();
+    };
+
+    // Streaming scan of tile points [0, npts) (global index base + i) through each query's filter.
+    auto stream_tile = [&](const float* tile, int base, int npts) {
         for (int i0 = 0; i0 < npts; i0 += 32) {
             const int i = i0 + lane;
             const bool valid = i < npts;
@@ -135,26 +164,101 @@ __global__ void __launch_bounds__(kKnnThreads)
                 const bool pass = valid && d <= thr[q];
                 const unsigned bal = __ballot_sync(kFull, pass);
                 if (bal == 0) continue;
-                unsigned long long* cb = s_cand[warp][q];
-                if (pass) {
-                    cb[cnt[q] + __popc(bal & lt_mask)] =
-                        (static_cast<unsigned long long>(__float_as_uint(d)) << 32) | static_cast<unsigned>(base + i);
-                }
+                if (pass) s_cand[warp][q][cnt[q] + __popc(bal & lt_mask)] = make_key(d, static_cast<unsigned>(base + i));
                 cnt[q] += __popc(bal);
-                if (cnt[q] >= 32) {
-                    __syncwarp();
-                    unsigned long long c = cb[lane];
-                    const int rem = cnt[q] - 32;
-                    const unsigned long long r = lane < rem ? cb[32 + lane] : 0ull;
-                    __syncwarp();
-                    if (lane < rem) cb[lane] = r;
-                    cnt[q] = rem;
-                    c = bitonic_sort32(c, lane);
-                    top[q] = merge_sorted32(top[q], c, lane);
-                    thr[q] = __uint_as_float(static_cast<unsigned>(__shfl_sync(kFull, top[q], k - 1) >> 32));
-                    __syncwarp();
-                }
+                if (cnt[q] >= 32) flush32(q);
             }
+        }
+    };
+
+    for (int t = 0; t < ntiles; ++t) {
+        if (use_bulk) {
+            mbar_wait(&s_full[t & 1], (t >> 1) & 1);
+        } else {
+            __syncthreads();
+        }
+        const float* tile = s_tile[t & 1];
+        const int base = t * kKnnTile;
+        const int npts = min(kKnnTile, N - base);
+        if (t == 0) {
+            // ---------------- bootstrap on the first tile, one query at a time (reuses the 32 d registers)
+            bool fallback = false;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                if (!act[q] || fallback) continue;
+                float d[32];
+                float m1 = __uint_as_float(kInfBits), m2 = m1;
+#pragma unroll
+                for (int s = 0; s < 32; ++s) {
+                    d[s] = __uint_as_float(kInfBits);
+                    if (s * 32 < npts) {  // warp-uniform
+                        const int i = s * 32 + lane;
+                        const int ii = i < npts ? i : 0;
+                        const float v = sumsq_acc(tile[3 * ii] - qx[q], tile[3 * ii + 1] - qy[q], tile[3 * ii + 2] - qz[q]);
+                        d[s] = i < npts ? v : __uint_as_float(kInfBits);
+                        m2 = fminf(m2, fmaxf(m1, d[s]));
+                        m1 = fminf(m1, d[s]);
+                    }
+                }
+                // T = k-th smallest of the 64 per-lane minima (bit patterns of non-negative floats order like uints)
+                const unsigned a = bitonic_sort32(__float_as_uint(m1), lane);
+                const unsigned c2 = bitonic_sort32(__float_as_uint(m2), lane);
+                const unsigned rev = __shfl_sync(kFull, c2, 31 - lane);
+                unsigned low = a < rev ? a : rev;  // the 32 smallest of the 64, bitonic
+                unsigned tb;
+                if (k == 32) {
+                    tb = __reduce_max_sync(kFull, low);
+                } else {
+                    low = bitonic_merge32(low, lane);
+                    tb = __shfl_sync(kFull, low, k - 1);
+                }
+                const float T = __uint_as_float(tb);
+                int mine = 0;
+#pragma unroll
+                for (int s = 0; s < 32; ++s) mine += (s * 32 + lane < npts) && (d[s] <= T);
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int total = __shfl_sync(kFull, incl, 31);
+                if (total > 64) {  // heavy ties: let the streaming path handle this tile for every query
+                    fallback = true;
+                    continue;
+                }
+                u64* cb = s_cand[warp][q];
+                int off = incl - mine;
+#pragma unroll
+                for (int s = 0; s < 32; ++s) {
+                    if ((s * 32 + lane < npts) && (d[s] <= T)) cb[off++] = make_key(d[s], static_cast<unsigned>(s * 32 + lane));
+                }
+                __syncwarp();
+                u64 c = lane < total ? cb[lane] : kKeyInf;
+                c = bitonic_sort32(c, lane);
+                const int extra = total - 32;
+                if (extra > 8) {
+                    u64 c1 = 32 + lane < total ? cb[32 + lane] : kKeyInf;
+                    c1 = bitonic_sort32(c1, lane);
+                    c = merge_sorted32(c, c1, lane);
+                } else {
+                    for (int e = 0; e < extra; ++e) c = insert_sorted32(c, cb[32 + e], lane);
+                }
+                top[q] = c;
+                thr[q] = __uint_as_float(static_cast<unsigned>(__shfl_sync(kFull, c, k - 1) >> 32));
+                __syncwarp();
+            }
+            if (fallback) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    thr[q] = __uint_as_float(kInfBits);
+                    top[q] = kKeyInf;
+                    cnt[q] = 0;
+                }
+                stream_tile(tile, base, npts);
+            }
+        } else {
+            stream_tile(tile, base, npts);
         }
         __syncthreads();  // every warp is done with this buffer
         if (t + 2 < ntiles) load_tile(t + 2);
@@ -165,7 +269,7 @@ __global__ void __launch_bounds__(kKnnThreads)
         if (!act[q]) continue;
         if (cnt[q] > 0) {
             __syncwarp();
-            unsigned long long c = lane < cnt[q] ? s_cand[warp][q][lane] : kKeyInf;
+            u64 c = lane < cnt[q] ? s_cand[warp][q][lane] : kKeyInf;
             c = bitonic_sort32(c, lane);
             top[q] = merge_sorted32(top[q], c, lane);
         }
@@ -195,8 +299,9 @@ static int launch_knn_group(const float* ref, const float* query, int B, int N, 
                             int64_t* idx, float* nbhd, float* nbhd_org, cudaStream_t st) {
     if (B > 65535) return GM3D_ENOSUP;
     const int use_bulk = (N % 4 == 0) && (reinterpret_cast<uintptr_t>(ref) % 16 == 0);
-    // queries per warp: keep >= ~2 waves of CTAs when the problem allows it
-    int q = 4;
+    // queries per warp: share each streamed tile between more queries when the cloud is large, but keep
+    // at least ~2 waves of CTAs
+    int q = N > kKnnTile ? 4 : 1;
     while (q > 1 && static_cast<long long>(B) * ((G + kKnnWarps * q - 1) / (kKnnWarps * q)) < 2 * 148) q >>= 1;
     dim3 grid((G + kKnnWarps * q - 1) / (kKnnWarps * q), B);
     switch (q) {

@@ -1,12 +1,10 @@
 // Small data-movement / selection kernels of the path: gather_operation (+grad), hard-patch mask
-// selection (generate_mask / _mask_center_rand), boolean-mask patch select and the per-rank loss
-// statistics vector that feeds the one all-reduce of a step.
+// selection (generate_mask / _mask_center_rand) with the masked-patch index list fused in, and the
+// stand-alone boolean-mask patch select.
 //
 // Reference call sites (/root/reference/Point-MAE_SA3D): utils/miscc.py:19 (gather_operation);
 // ..._feature_besed.py:1062-1109 and models/Point_MAE.py:297-320 (masks); models/Point_MAE.py:425 and
-// ..._Classifier_SVM.py:972 (`neighborhood[mask]`); util/misc.py:345-353 (all_reduce_mean).
-#include <float.h>
-
+// ..._Classifier_SVM.py:972 (`neighborhood[mask]`).
 #include "common.cuh"
 
 namespace gm3d {
@@ -66,49 +64,84 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t ctr) {
     return static_cast<float>(c[0] >> 8) * (1.0f / 16777216.0f);
 }
 
-// ---------------------------------------------------------------- hard-patch mask
-// One CTA per row.  Rank-based selection (O(L^2) compares, L is 64..512): an element is in the top
-// len_loss iff fewer than len_loss elements are larger in (value, index) order; the random remainder is
-// ranked the same way on its keys among the non-top elements.
-__global__ void __launch_bounds__(256)
-    hard_mask_kernel(const float* __restrict__ loss_pred, int L, int len_keep, int len_loss,
-                     const float* __restrict__ rand_keys, uint64_t seed, uint64_t offset, uint8_t* __restrict__ mask) {
-    extern __shared__ unsigned char smem_raw[];
-    float* s_lp = reinterpret_cast<float*>(smem_raw);
-    float* s_rk = s_lp + L;
-    uint8_t* s_top = reinterpret_cast<uint8_t*>(s_rk + L);
-    const int b = blockIdx.x;
+// ---------------------------------------------------------------- hard-patch mask (+ masked-patch index list)
+// Order-preserving map float -> uint32 (total order of the finite floats, -0 < +0).
+__device__ __forceinline__ unsigned ord_bits(float f) {
+    const unsigned u = __float_as_uint(__fadd_rn(f, 0.0f));  // -0 -> +0 so that equal values get equal bits
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// Ascending bitonic sort of LP (power of two) 64-bit keys in shared memory by the whole CTA.
+__device__ void smem_bitonic_sort(unsigned long long* key, int LP) {
+    for (int sz = 2; sz <= LP; sz <<= 1) {
+        for (int st = sz >> 1; st > 0; st >>= 1) {
+            for (int t = threadIdx.x; t < LP / 2; t += blockDim.x) {
+                const int i = ((t / st) * (st << 1)) + (t % st);
+                const int j = i + st;
+                const bool up = (i & sz) == 0;
+                const unsigned long long a = key[i], c = key[j];
+                if ((a > c) == up) {
+                    key[i] = c;
+                    key[j] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// One CTA per row.  Keys are (ordered value bits << 32 | index): ascending key order == stable ascending
+// value order, so "the len_loss largest, ties -> higher index larger" is the tail of the sorted array.
+// Pass 1 selects the top len_loss by loss_pred, pass 2 the top n_rand by random key among the rest; then
+// the row's mask is written and (optionally) compacted in order into patch_index.
+__global__ void __launch_bounds__(1024)
+    hard_mask_kernel(const float* __restrict__ loss_pred, int L, int LP, int len_keep, int len_loss,
+                     const float* __restrict__ rand_keys, uint64_t seed, uint64_t offset, uint8_t* __restrict__ mask,
+                     int32_t* __restrict__ patch_index) {
+    extern __shared__ __align__(8) unsigned char smem_raw[];
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw);
+    uint8_t* s_sel = reinterpret_cast<uint8_t*>(s_key + LP);
+    const int b = blockIdx.x, tid = threadIdx.x;
     const int n_rand = L - len_keep - len_loss;
-    for (int i = threadIdx.x; i < L; i += blockDim.x) {
-        s_lp[i] = len_loss > 0 ? __ldg(loss_pred + static_cast<size_t>(b) * L + i) : 0.0f;
-        s_rk[i] = rand_keys ? __ldg(rand_keys + static_cast<size_t>(b) * L + i)
-                            : philox_uniform(seed, offset + static_cast<uint64_t>(b) * L + i);
+    const int M = L - len_keep;
+
+    for (int i = tid; i < LP; i += blockDim.x) {
+        s_sel[i] = 0;
+        s_key[i] = (i < L && len_loss > 0)
+                       ? (static_cast<unsigned long long>(ord_bits(__ldg(loss_pred + static_cast<size_t>(b) * L + i))) << 32) | static_cast<unsigned>(i)
+                       : 0ull;  // pads sort to the front
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < L; i += blockDim.x) {
-        int larger = 0;
-        if (len_loss > 0) {
-            const float v = s_lp[i];
-            for (int j = 0; j < L; ++j) {
-                const float w = s_lp[j];
-                larger += (w > v) || (w == v && j > i);
-            }
-        }
-        s_top[i] = len_loss > 0 && larger < len_loss;
+    if (len_loss > 0) {
+        smem_bitonic_sort(s_key, LP);
+        for (int t = tid; t < len_loss; t += blockDim.x) s_sel[static_cast<unsigned>(s_key[LP - 1 - t] & 0xffffffffu)] = 1;
+        __syncthreads();
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < L; i += blockDim.x) {
-        uint8_t out = s_top[i];
-        if (!out && n_rand > 0) {
-            const float v = s_rk[i];
-            int larger = 0;
-            for (int j = 0; j < L; ++j) {
-                const float w = s_rk[j];
-                larger += !s_top[j] && ((w > v) || (w == v && j > i));
+    if (n_rand > 0) {
+        for (int i = tid; i < LP; i += blockDim.x) {
+            unsigned long long kkey = 0ull;  // pads and already-selected patches sort to the front
+            if (i < L && !s_sel[i]) {
+                const float r = rand_keys ? __ldg(rand_keys + static_cast<size_t>(b) * L + i)
+                                          : philox_uniform(seed, offset + static_cast<uint64_t>(b) * L + i);
+                kkey = (static_cast<unsigned long long>(ord_bits(r)) << 32) | static_cast<unsigned>(i);
             }
-            out = larger < n_rand;
+            s_key[i] = kkey;
         }
-        mask[static_cast<size_t>(b) * L + i] = out;
+        __syncthreads();
+        smem_bitonic_sort(s_key, LP);
+        for (int t = tid; t < n_rand; t += blockDim.x) s_sel[static_cast<unsigned>(s_key[LP - 1 - t] & 0xffffffffu)] = 1;
+        __syncthreads();
+    }
+    for (int i = tid; i < L; i += blockDim.x) mask[static_cast<size_t>(b) * L + i] = s_sel[i];
+    if (patch_index && tid < 32) {  // ordered compaction by warp 0
+        int base = 0;
+        for (int c0 = 0; c0 < L; c0 += 32) {
+            const int i = c0 + tid;
+            const bool sel = i < L && s_sel[i];
+            const unsigned bal = __ballot_sync(kFull, sel);
+            if (sel) patch_index[static_cast<size_t>(b) * M + base + __popc(bal & ((1u << tid) - 1u))] = b * L + i;
+            base += __popc(bal);
+        }
     }
 }
 
@@ -159,40 +192,6 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// ---------------------------------------------------------------- loss statistics
-__global__ void __launch_bounds__(1024) loss_stats_kernel(const float* __restrict__ v, int P, float* __restrict__ stats) {
-    __shared__ double s_sum[1024], s_sq[1024];
-    __shared__ float s_min[1024], s_max[1024];
-    double sum = 0.0, sq = 0.0;
-    float mn = FLT_MAX, mx = -FLT_MAX;
-    for (int i = threadIdx.x; i < P; i += 1024) {
-        const float x = v[i];
-        sum += x;
-        sq += static_cast<double>(x) * x;
-        mn = fminf(mn, x);
-        mx = fmaxf(mx, x);
-    }
-    s_sum[threadIdx.x] = sum, s_sq[threadIdx.x] = sq, s_min[threadIdx.x] = mn, s_max[threadIdx.x] = mx;
-    __syncthreads();
-    for (int o = 512; o > 0; o >>= 1) {
-        if (threadIdx.x < o) {
-            s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
-            s_sq[threadIdx.x] += s_sq[threadIdx.x + o];
-            s_min[threadIdx.x] = fminf(s_min[threadIdx.x], s_min[threadIdx.x + o]);
-            s_max[threadIdx.x] = fmaxf(s_max[threadIdx.x], s_max[threadIdx.x + o]);
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        stats[0] = static_cast<float>(s_sum[0]);
-        stats[1] = static_cast<float>(s_sq[0]);
-        stats[2] = static_cast<float>(P);
-        stats[3] = s_min[0];
-        stats[4] = s_max[0];
-        stats[5] = stats[6] = stats[7] = 0.0f;
-    }
-}
-
 }  // namespace gm3d
 
 GM3D_API int gm3d_gather_f32(const float* feat, const int32_t* idx, int B, int C, int N, int G, float* out,
@@ -214,14 +213,19 @@ GM3D_API int gm3d_gather_grad_f32(const float* gout, const int32_t* idx, int B, 
 }
 
 GM3D_API int gm3d_hard_mask_f32(const float* loss_pred, int B, int L, int len_keep, int len_loss,
-                                const float* rand_keys, uint64_t seed, uint64_t offset, uint8_t* mask, void* stream) {
+                                const float* rand_keys, uint64_t seed, uint64_t offset, uint8_t* mask,
+                                int32_t* patch_index, void* stream) {
     using namespace gm3d;
     if (!mask || B <= 0 || L <= 0 || len_keep < 0 || len_keep > L || len_loss < 0 || len_loss > L - len_keep)
         return GM3D_EINVAL;
     if (len_loss > 0 && !loss_pred) return GM3D_EINVAL;
     if (L > 4096) return GM3D_ENOSUP;
-    const size_t smem = static_cast<size_t>(L) * 9;
-    hard_mask_kernel<<<B, 256, smem, as_stream(stream)>>>(loss_pred, L, len_keep, len_loss, rand_keys, seed, offset, mask);
+    int LP = 2;
+    while (LP < L) LP <<= 1;
+    int threads = LP / 2 < 32 ? 32 : (LP / 2 > 1024 ? 1024 : LP / 2);
+    const size_t smem = static_cast<size_t>(LP) * 9;
+    hard_mask_kernel<<<B, threads, smem, as_stream(stream)>>>(loss_pred, L, LP, len_keep, len_loss, rand_keys, seed, offset,
+                                                             mask, patch_index);
     return launch_status();
 }
 
@@ -234,12 +238,5 @@ GM3D_API int gm3d_select_patches_f32(const float* nbhd, const uint8_t* mask, int
     if (static_cast<size_t>(M) * 4 > 40 * 1024) return GM3D_ENOSUP;
     select_patches_kernel<<<B, 256, static_cast<size_t>(M) * 4, as_stream(stream)>>>(nbhd, mask, G, row_floats, M,
                                                                                      invert, out, patch_index, status);
-    return launch_status();
-}
-
-GM3D_API int gm3d_loss_stats_f32(const float* per_patch, int P, float* stats, void* stream) {
-    using namespace gm3d;
-    if (!per_patch || !stats || P <= 0) return GM3D_EINVAL;
-    loss_stats_kernel<<<1, 1024, 0, as_stream(stream)>>>(per_patch, P, stats);
     return launch_status();
 }

@@ -13,7 +13,7 @@ from . import _lib
 
 __all__ = [
     "furthest_point_sample", "fps_centers", "gather", "gather_grad", "knn", "group", "chamfer_forward",
-    "chamfer_backward", "select_patches", "hard_mask", "loss_stats",
+    "chamfer_fused", "chamfer_backward", "select_patches", "hard_mask", "loss_stats",
 ]
 
 
@@ -148,10 +148,14 @@ def group(xyz: torch.Tensor, num_group: int, group_size: int, want_org: bool = F
     return {"neighborhood": nb, "center": center, "neighborhood_org": nb_org, "knn_idx": knn_idx, "fps_idx": fps_idx}
 
 
-def chamfer_forward(xyz1: torch.Tensor, xyz2: torch.Tensor, norm: int = 2, want_per_patch: bool = False,
-                    want_total: bool = False, xyz2_index: Optional[torch.Tensor] = None):
-    """xyz1 (P,n,3), xyz2 (P,m,3) [or the patch pool + xyz2_index (P,) int32] ->
-    dist1 (P,n), dist2 (P,m), idx1, idx2 (int32), per_patch (P,) or None, total (1,) or None."""
+def _chamfer_ws(P: int, dev) -> torch.Tensor:
+    """Zero-initialised workspace of the Chamfer forward (ticket + per-patch scratch); the kernel leaves the
+    ticket zeroed, so a cached workspace could be reused -- a fresh torch.zeros keeps the wrapper stateless."""
+    n = _lib.load().gm3d_workspace_bytes(_lib.OP_CHAMFER_FWD, P, 0, 0, 0)
+    return torch.zeros(n, dtype=torch.uint8, device=dev)
+
+
+def _chamfer_args(xyz1, xyz2, xyz2_index):
     _req(xyz1, "xyz1", torch.float32, 3)
     _req(xyz2, "xyz2", torch.float32, 3)
     if xyz1.shape[2] != 3 or xyz2.shape[2] != 3:
@@ -164,19 +168,60 @@ def chamfer_forward(xyz1: torch.Tensor, xyz2: torch.Tensor, norm: int = 2, want_
             raise ValueError("xyz2_index must have one entry per xyz1 patch")
     elif xyz2.shape[0] != P:
         raise ValueError("xyz1 and xyz2 disagree on the number of patches")
+    return P, n, m
+
+
+def chamfer_forward(xyz1: torch.Tensor, xyz2: torch.Tensor, norm: int = 2, want_per_patch: bool = False,
+                    want_total: bool = False, xyz2_index: Optional[torch.Tensor] = None, want_stats: bool = False):
+    """xyz1 (P,n,3), xyz2 (P,m,3) [or the patch pool + xyz2_index (P,) int32] ->
+    dist1 (P,n), dist2 (P,m), idx1, idx2 (int32), per_patch (P,) or None, total (1,) or None[, stats (8,)]."""
+    P, n, m = _chamfer_args(xyz1, xyz2, xyz2_index)
     dev = xyz1.device
     with torch.cuda.device(dev):
         d1 = torch.empty((P, n), dtype=torch.float32, device=dev)
         d2 = torch.empty((P, m), dtype=torch.float32, device=dev)
         i1 = torch.empty((P, n), dtype=torch.int32, device=dev)
         i2 = torch.empty((P, m), dtype=torch.int32, device=dev)
-        pp = torch.empty((P,), dtype=torch.float32, device=dev) if (want_per_patch or want_total) else None
+        reduce = want_total or want_stats
+        pp = torch.empty((P,), dtype=torch.float32, device=dev) if (want_per_patch or reduce) else None
         tot = torch.empty((1,), dtype=torch.float32, device=dev) if want_total else None
+        stats = torch.empty((_lib.LOSS_STATS_LEN,), dtype=torch.float32, device=dev) if want_stats else None
         if P > 0 and n > 0 and m > 0:
+            ws = _chamfer_ws(P, dev) if reduce else None
             rc = _lib.load().gm3d_chamfer_fwd_f32(_p(xyz1), _p(xyz2), _p(xyz2_index), P, n, m, _p(d1), _p(d2), _p(i1),
-                                                  _p(i2), _p(pp), _p(tot), int(norm), None, _stream(xyz1))
+                                                  _p(i2), _p(pp), _p(tot), _p(stats), int(norm), _p(ws), _stream(xyz1))
             _lib.check("gm3d_chamfer_fwd_f32", rc)
+    if want_stats:
+        return d1, d2, i1, i2, pp, tot, stats
     return d1, d2, i1, i2, pp, tot
+
+
+def chamfer_fused(xyz1: torch.Tensor, xyz2: torch.Tensor, gscale1: float, gscale2: float, norm: int = 2,
+                  want_grad2: bool = False, xyz2_index: Optional[torch.Tensor] = None, want_dist: bool = False):
+    """Forward + backward of the mean-reduced Chamfer loss in one launch (n, m <= 32).
+    Returns dict(per_patch (P,), total (1,), stats (8,), grad1 (P,n,3), grad2 or None[, dist1, dist2, idx1, idx2])."""
+    P, n, m = _chamfer_args(xyz1, xyz2, xyz2_index)
+    if xyz2_index is not None and want_grad2:
+        raise ValueError("grad_xyz2 is not defined for an indexed (shared) xyz2 pool")
+    dev = xyz1.device
+    e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)  # noqa: E731
+    with torch.cuda.device(dev):
+        out = {"per_patch": e((P,), torch.float32), "total": e((1,), torch.float32),
+               "stats": e((_lib.LOSS_STATS_LEN,), torch.float32), "grad1": e((P, n, 3), torch.float32),
+               "grad2": e((P, m, 3), torch.float32) if want_grad2 else None,
+               "dist1": e((P, n), torch.float32) if want_dist else None,
+               "dist2": e((P, m), torch.float32) if want_dist else None,
+               "idx1": e((P, n), torch.int32) if want_dist else None,
+               "idx2": e((P, m), torch.int32) if want_dist else None}
+        if P > 0 and n > 0 and m > 0:
+            ws = _chamfer_ws(P, dev)
+            rc = _lib.load().gm3d_chamfer_fused_f32(_p(xyz1), _p(xyz2), _p(xyz2_index), P, n, m, float(gscale1),
+                                                    float(gscale2), _p(out["dist1"]), _p(out["dist2"]), _p(out["idx1"]),
+                                                    _p(out["idx2"]), _p(out["per_patch"]), _p(out["total"]),
+                                                    _p(out["stats"]), int(norm), _p(out["grad1"]), _p(out["grad2"]),
+                                                    _p(ws), _stream(xyz1))
+            _lib.check("gm3d_chamfer_fused_f32", rc)
+    return out
 
 
 def chamfer_backward(xyz1, xyz2, idx1, idx2, gdist1, gdist2, want_grad2: bool = True,
@@ -240,8 +285,9 @@ def select_patches(nbhd: Optional[torch.Tensor], mask: torch.Tensor, num_selecte
 
 def hard_mask(loss_pred: Optional[torch.Tensor], B: int, L: int, len_keep: int, len_loss: int,
               rand_keys: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0,
-              device: Optional[torch.device] = None) -> torch.Tensor:
-    """(B,L) uint8 mask, 1 = masked, exactly L - len_keep ones per row (include/gm3d.h)."""
+              device: Optional[torch.device] = None, want_index: bool = False):
+    """(B,L) uint8 mask, 1 = masked, exactly L - len_keep ones per row (include/gm3d.h).
+    want_index: also return patch_index (B*(L-len_keep),) int32 = flat ids b*L+i of the masked patches in order."""
     if loss_pred is not None:
         _req(loss_pred, "loss_pred", torch.float32, 2)
         device = loss_pred.device
@@ -255,16 +301,17 @@ def hard_mask(loss_pred: Optional[torch.Tensor], B: int, L: int, len_keep: int, 
         raise RuntimeError("hard_mask runs on CUDA only (gm3d_b200 has no CPU fallback)")
     with torch.cuda.device(device):
         mask = torch.empty((B, L), dtype=torch.uint8, device=device)
+        index = torch.empty((B * (L - int(len_keep)),), dtype=torch.int32, device=device) if want_index else None
         if B > 0 and L > 0:
             rc = _lib.load().gm3d_hard_mask_f32(_p(loss_pred), B, L, int(len_keep), int(len_loss), _p(rand_keys),
-                                                int(seed) & (2**64 - 1), int(offset) & (2**64 - 1), _p(mask),
+                                                int(seed) & (2**64 - 1), int(offset) & (2**64 - 1), _p(mask), _p(index),
                                                 torch.cuda.current_stream(device).cuda_stream)
             _lib.check("gm3d_hard_mask_f32", rc)
-    return mask
+    return (mask, index) if want_index else mask
 
 
 def loss_stats(per_patch: torch.Tensor) -> torch.Tensor:
-    """per_patch (P,) -> stats (8,) = [sum, sum_sq, count, min, max, 0, 0, 0] for the step's one all-reduce."""
+    """per_patch (P,) -> stats (8,) = [sum, sum_sq, count, min, max, mean, 0, 0] for the step's one all-reduce."""
     _req(per_patch, "per_patch", torch.float32)
     with torch.cuda.device(per_patch.device):
         stats = torch.empty((_lib.LOSS_STATS_LEN,), dtype=torch.float32, device=per_patch.device)

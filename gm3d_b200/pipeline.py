@@ -8,7 +8,7 @@
 
 This is the per-step sequence of the reference's pre-training loop restricted to the hot path
 (/root/reference/Point-MAE_SA3D/engine_pretrain_Classifier_SVM.py:108-118,157-184,297-305).  The step issues
-8 kernels through the C ABI; replayed as one graph it has no host work between them.  `HostStagedStep`
+4 kernels through the C ABI; replayed as one graph it has no host work between them.  `HostStagedStep`
 adds the host<->device copies from/to pinned memory (the end-to-end arm of bench.py).
 """
 from __future__ import annotations
@@ -20,7 +20,7 @@ import torch
 from . import _lib
 from .masking import mask_lengths
 
-KERNELS_PER_STEP = 8  # fps, knn_group, hard_mask, select, chamfer_fwd, mean_reduce, chamfer_bwd, loss_stats
+KERNELS_PER_STEP = 4  # fps, knn_group, hard_mask (+patch index), chamfer fused (fwd + bwd + loss reduction)
 
 
 class GroupLossStep:
@@ -57,6 +57,8 @@ class GroupLossStep:
         self.status = torch.zeros((1,), dtype=i32, device=d)
         ws = self.lib.gm3d_workspace_bytes(_lib.OP_GROUP, B, N, G, k)
         self.ws = e((ws,), torch.uint8) if ws else None
+        self.cd_ws = torch.zeros((self.lib.gm3d_workspace_bytes(_lib.OP_CHAMFER_FWD, self.P, k, k, 0),),
+                                 dtype=torch.uint8, device=d)  # ticket must start at zero; the kernel re-zeroes it
         self.graph: Optional[torch.cuda.CUDAGraph] = None
 
     # algorithmic HBM bytes of one step per cloud (SURVEY App. B formulas; DESIGN.md "Roofline accounting")
@@ -65,13 +67,13 @@ class GroupLossStep:
         return {
             "fps": 12 * N + 16 * G,
             "knn_group": 12 * N + 12 * G + 12 * G * k,           # int64 idx not requested by Group
-            "chamfer_fwd": 24 * M * k + 16 * M * k + 4 * M,
-            "chamfer_bwd": 12 * M * k * 2 + 8 * M * k + 12 * M * k,  # read both clouds + idx, write grad_pred
-            "mask_select": 5 * G + 4 * M,
+            # fused fwd+bwd: read pred + target patches once, write dist1/2 + idx1/2, per-patch loss, grad_pred
+            "chamfer_fused": 24 * M * k + 16 * M * k + 4 * M + 12 * M * k,
+            "hard_mask": 5 * G + 4 * M,
         }
 
     def enqueue(self, stream: Optional[int] = None) -> None:
-        """Enqueue the 8 kernels of one step on `stream` (default: torch's current stream)."""
+        """Enqueue the kernels of one step on `stream` (default: torch's current stream)."""
         L, p = self.lib, (lambda t: None if t is None else t.data_ptr())
         st = torch.cuda.current_stream(self.dev).cuda_stream if stream is None else stream
         B, N, G, k, P = self.B, self.N, self.G, self.k, self.P
@@ -79,17 +81,12 @@ class GroupLossStep:
         chk("gm3d_group_f32", L.gm3d_group_f32(p(self.xyz), B, N, G, k, p(self.fps_idx), p(self.center), None,
                                                p(self.neighborhood), None, p(self.ws), st))
         chk("gm3d_hard_mask_f32", L.gm3d_hard_mask_f32(p(self.loss_pred), B, G, self.len_keep, self.len_loss, None,
-                                                       self.seed, self.rand_offset, p(self.mask), st))
-        chk("gm3d_select_patches_f32", L.gm3d_select_patches_f32(None, p(self.mask), B, G, k * 3, self.M, 0, None,
-                                                                 p(self.patch_index), p(self.status), st))
-        chk("gm3d_chamfer_fwd_f32", L.gm3d_chamfer_fwd_f32(p(self.pred), p(self.neighborhood), p(self.patch_index), P, k, k,
-                                                           p(self.dist1), p(self.dist2), p(self.idx1), p(self.idx2),
-                                                           p(self.per_patch), p(self.total), self.norm, None, st))
-        g = 1.0 / (P * k)  # d mean(dist1)/d dist1[p,i]
-        chk("gm3d_chamfer_bwd_f32", L.gm3d_chamfer_bwd_f32(p(self.pred), p(self.neighborhood), p(self.patch_index),
-                                                           p(self.idx1), p(self.idx2), None, None, g, g, P, k, k,
-                                                           p(self.grad_pred), None, st))
-        chk("gm3d_loss_stats_f32", L.gm3d_loss_stats_f32(p(self.per_patch), P, p(self.stats), st))
+                                                       self.seed, self.rand_offset, p(self.mask), p(self.patch_index), st))
+        g = (1.0 if self.norm == 2 else 0.5) / (P * k)  # d mean / d dist (L1: the outer /2 folded in)
+        chk("gm3d_chamfer_fused_f32", L.gm3d_chamfer_fused_f32(
+            p(self.pred), p(self.neighborhood), p(self.patch_index), P, k, k, g, g, p(self.dist1), p(self.dist2),
+            p(self.idx1), p(self.idx2), p(self.per_patch), p(self.total), p(self.stats), self.norm, p(self.grad_pred),
+            None, p(self.cd_ws), st))
 
     def capture(self, extra=None) -> "GroupLossStep":
         """Capture one step (plus `extra()`, e.g. the stats all-reduce) into a CUDA graph."""

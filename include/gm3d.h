@@ -16,6 +16,7 @@
  *   gm3d_group_f32          Group.forward (fps -> knn -> gather -> centre)   models/Point_MAE.py:57-78,
  *                                                                   ..._feature_besed.py:1238-1260
  *   gm3d_chamfer_fwd_f32    chamfer.forward  (ChamferFunction)      models/Point_MAE.py:390-397,426
+ *   gm3d_chamfer_fused_f32  chamfer.forward + backward of the mean  models/Point_MAE.py:426 + tools/runner_pretrain.py:138
  *   gm3d_chamfer_bwd_f32    chamfer.backward (ChamferFunction)      tools/runner_pretrain.py:138-151
  *   gm3d_select_patches_f32 `neighborhood[mask].reshape(B*M,-1,3)`  models/Point_MAE.py:425,
  *                                                                   ..._Classifier_SVM.py:972
@@ -109,12 +110,29 @@ int gm3d_group_f32(const float* xyz, int B, int N, int G, int k, int32_t* fps_id
  * idx1 (P,n), idx2 (P,m) int32 arg-min (lowest index on ties).  Optional fused reductions:
  *   per_patch (P): norm 2 -> mean_n dist1 + mean_m dist2;  norm 1 -> (mean_n sqrt dist1 + mean_m sqrt dist2)/2
  *   total (1):     mean over patches of per_patch (= ChamferDistanceL2 / L1 scalar), deterministic.
+ *   stats (8):     [sum, sum of squares, count, min, max, mean, 0, 0] of per_patch (see gm3d_loss_stats_f32).
+ * total / stats need the workspace (gm3d_workspace_bytes(GM3D_OP_CHAMFER_FWD, P, n, m, 0) bytes) whose first
+ * 16 bytes must be ZERO before the first launch that uses it; the library leaves them zero (the last CTA
+ * to finish does the reduction and resets its ticket), so one cudaMemset at allocation is enough.
  * xyz2_index (P) int32 or NULL: when given, patch p of xyz2 is read from xyz2 + xyz2_index[p]*m*3
  * (the masked-patch select `neighborhood[mask]` folded into the load). */
 int gm3d_chamfer_fwd_f32(const float* xyz1, const float* xyz2, const int32_t* xyz2_index /* or NULL */, int P,
                          int n, int m, float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
-                         float* per_patch /* or NULL */, float* total /* or NULL */, int norm /* 1|2 */, void* ws,
+                         float* per_patch /* or NULL */, float* total /* or NULL */,
+                         float* stats /* GM3D_LOSS_STATS_LEN floats or NULL */, int norm /* 1|2 */, void* ws,
                          void* stream);
+
+/* Forward AND backward of the mean-reduced Chamfer loss in one launch (patch regime n, m <= 32 only,
+ * else GM3D_ENOSUP): the upstream gradient of a mean is uniform and known at launch, so the kernel
+ * that finds the arg-mins also emits the gradients and nothing is re-read.
+ *   L2 (norm 2): d loss / d dist1[p,i] = gscale1, d loss / d dist2[p,j] = gscale2
+ *                (ChamferDistanceL2: gscale1 = g/(P n), gscale2 = g/(P m) for an upstream scalar g)
+ *   L1 (norm 1): d loss / d dist1[p,i] = gscale1 * 0.5 / sqrt(dist1[p,i])  (gscale1 = g/(2 P n)), dist2 likewise
+ * dist1, dist2, idx1, idx2, per_patch, total, stats and gxyz2 may each be NULL; gxyz1 is required. */
+int gm3d_chamfer_fused_f32(const float* xyz1, const float* xyz2, const int32_t* xyz2_index /* or NULL */, int P,
+                           int n, int m, float gscale1, float gscale2, float* dist1, float* dist2, int32_t* idx1,
+                           int32_t* idx2, float* per_patch, float* total, float* stats, int norm /* 1|2 */,
+                           float* gxyz1, float* gxyz2 /* or NULL */, void* ws, void* stream);
 
 /* Chamfer backward, atomics-free and deterministic.  With g1[p,i] = gscale1 * gdist1[p,i] (or gscale1
  * alone when gdist1 is NULL -- the uniform upstream gradient of a mean), g2 likewise:
@@ -140,10 +158,11 @@ int gm3d_select_patches_f32(const float* nbhd, const uint8_t* mask, int B, int G
  * from Philox4x32-10(seed; counter = offset + b*L + i).  len_loss = 0 is the plain random mask. */
 int gm3d_hard_mask_f32(const float* loss_pred /* may be NULL iff len_loss == 0 */, int B, int L, int len_keep,
                        int len_loss, const float* rand_keys /* or NULL */, uint64_t seed, uint64_t offset,
-                       uint8_t* mask, void* stream);
+                       uint8_t* mask, int32_t* patch_index /* (B*(L-len_keep)) flat ids b*L+i in order, or NULL */,
+                       void* stream);
 
 /* Per-rank loss statistics for the one small all-reduce of a step.  per_patch (P) ->
- * stats[GM3D_LOSS_STATS_LEN] = { sum, sum of squares, count, min, max, 0, 0, 0 } (deterministic). */
+ * stats[GM3D_LOSS_STATS_LEN] = { sum, sum of squares, count, min, max, mean, 0, 0 } (deterministic). */
 int gm3d_loss_stats_f32(const float* per_patch, int P, float* stats, void* stream);
 
 #ifdef __cplusplus

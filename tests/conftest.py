@@ -22,7 +22,7 @@ def synthetic_clouds(B, N, seed, kind="ball"):
     if kind == "ball":
         x = rng.standard_normal((B, N, 3))
         x -= x.mean(axis=1, keepdims=True)
-        x /= np.linalg.norm(x, axis=-1).max(axis=1)[:, None, None]
+        x /= np.maximum(np.linalg.norm(x, axis=-1).max(axis=1), 1e-12)[:, None, None]
         x = x * rng.uniform(2 / 3, 3 / 2, (B, 1, 3)) + rng.uniform(-0.2, 0.2, (B, 1, 3))
     elif kind == "sphere":
         x = rng.standard_normal((B, N, 3))
@@ -33,7 +33,7 @@ def synthetic_clouds(B, N, seed, kind="ball"):
             src = rng.integers(0, N, ndup)
             dst = rng.integers(0, N, ndup)
             x[b, dst] = x[b, src]
-            near = rng.integers(1, N, max(1, N // 200))
+            near = rng.integers(1, max(N, 2), max(1, N // 200)) % N
             x[b, near] = rng.uniform(-0.015, 0.015, (len(near), 3))
     else:
         raise ValueError(kind)

@@ -220,6 +220,65 @@ def test_chamfer_forward_backward(cuda, P, n, m):
     assert none is None and torch.equal(ga_only, ga)
 
 
+@pytest.mark.parametrize("P,n,m", [(4992, 32, 32), (1000, 16, 16), (777, 8, 8), (5, 20, 31), (3, 1, 1), (301, 32, 17)])
+def test_chamfer_fused_forward_backward(cuda, P, n, m):
+    """gm3d_chamfer_fused_f32 (fwd + bwd of the mean in one launch, loss reduced by the last CTA) against the
+    oracle: dist / idx exact, gradients bit-exact for L2 (same summation order), loss + stats within 1e-5."""
+    from gm3d_b200 import ops
+    rng = np.random.default_rng(P + n + m)
+    a = rng.standard_normal((P, n, 3)).astype(np.float32) * 0.1
+    b = (a + 0.02 * rng.standard_normal((P, n, 3))).astype(np.float32) if n == m else \
+        rng.standard_normal((P, m, 3)).astype(np.float32) * 0.1
+    w1, w2, wi1, wi2 = co.chamfer_fwd(a, b)
+    for norm in (2, 1):
+        gs1, gs2 = (1.0 / (P * n), 1.0 / (P * m)) if norm == 2 else (0.5 / (P * n), 0.5 / (P * m))
+        for rep in range(2):  # twice: the self-resetting ticket must leave the workspace reusable
+            r = ops.chamfer_fused(dev(a, cuda), dev(b, cuda), gs1, gs2, norm=norm, want_grad2=True, want_dist=True)
+        assert np.array_equal(host(r["dist1"]), w1) and np.array_equal(host(r["dist2"]), w2)
+        assert np.array_equal(host(r["idx1"]), wi1) and np.array_equal(host(r["idx2"]), wi2)
+        wpp = co.chamfer_per_patch(w1, w2, norm)
+        assert np.allclose(host(r["per_patch"]), wpp, rtol=RTOL, atol=0)
+        assert np.isclose(host(r["total"])[0], wpp.mean(), rtol=RTOL, atol=0)
+        st = host(r["stats"])
+        assert np.allclose(st[:6], [wpp.sum(), (wpp * wpp).sum(), P, wpp.min(), wpp.max(), wpp.mean()], rtol=RTOL)
+        if norm == 2:
+            g1 = np.full((P, n), np.float32(gs1), dtype=np.float32)
+            g2 = np.full((P, m), np.float32(gs2), dtype=np.float32)
+            wa, wb = co.chamfer_bwd(a, b, wi1, wi2, g1, g2)
+            assert np.array_equal(host(r["grad1"]), wa) and np.array_equal(host(r["grad2"]), wb)
+        else:
+            with np.errstate(divide="ignore"):
+                g1 = np.float32(gs1) * (np.float32(0.5) / np.sqrt(w1))
+                g2 = np.float32(gs2) * (np.float32(0.5) / np.sqrt(w2))
+            ok = np.isfinite(g1).all(axis=1) & np.isfinite(g2).all(axis=1)  # d == 0 -> inf upstream, as in torch
+            ta, tb = no.chamfer_bwd(a[ok], b[ok], wi1[ok], wi2[ok], g1[ok], g2[ok])
+            scale = max(np.abs(ta).max(), np.abs(tb).max()) if ok.any() else 1.0
+            assert np.abs(host(r["grad1"])[ok] - ta).max(initial=0) <= 1e-4 * scale
+            assert np.abs(host(r["grad2"])[ok] - tb).max(initial=0) <= 1e-4 * scale
+    # indexed target pool (masked-patch select folded into the load), grad w.r.t. the prediction only
+    if n == m:
+        pool = rng.standard_normal((2 * P, m, 3)).astype(np.float32) * 0.1
+        index = rng.permutation(2 * P)[:P].astype(np.int32)
+        r = ops.chamfer_fused(dev(a, cuda), dev(pool, cuda), 1.0 / (P * n), 1.0 / (P * m), xyz2_index=dev(index, cuda))
+        v1, v2, vi1, vi2 = co.chamfer_fwd(a, pool[index])
+        g = np.full((P, n), np.float32(1.0 / (P * n)), dtype=np.float32)
+        va, _ = co.chamfer_bwd(a, pool[index], vi1, vi2, g, g)
+        assert np.array_equal(host(r["grad1"]), va)
+        assert np.isclose(host(r["total"])[0], co.chamfer_per_patch(v1, v2, 2).mean(), rtol=RTOL)
+
+
+def test_hard_mask_patch_index(cuda):
+    from gm3d_b200 import ops
+    rng = np.random.default_rng(8)
+    for B, L, len_keep, len_loss in [(128, 64, 25, 15), (16, 512, 205, 100), (3, 33, 5, 7), (4, 64, 25, 0)]:
+        lp = rng.standard_normal((B, L)).astype(np.float32)
+        rk = rng.random((B, L)).astype(np.float32)
+        mask, index = ops.hard_mask(dev(lp, cuda), B, L, len_keep, len_loss, rand_keys=dev(rk, cuda), want_index=True)
+        want = co.hard_mask(lp, len_keep, len_loss, rk)
+        assert np.array_equal(host(mask), want)
+        assert np.array_equal(host(index), np.flatnonzero(want.reshape(-1)))
+
+
 def test_chamfer_modules_match_stock_autograd(cuda):
     """ChamferDistanceL2 / L1 / L2_split and their backward against a plain-PyTorch fp64 restatement."""
     from gm3d_b200.chamfer import ChamferDistanceL1, ChamferDistanceL2, ChamferDistanceL2_split, ChamferFunction
@@ -396,7 +455,8 @@ def test_loss_stats(cuda):
     v = torch.rand(4992, device=cuda)
     s = host(ops.loss_stats(v))
     h = host(v).astype(np.float64)
-    assert np.allclose(s[:5], [h.sum(), (h * h).sum(), 4992, h.min(), h.max()], rtol=1e-6)
+    assert np.allclose(s[:6], [h.sum(), (h * h).sum(), 4992, h.min(), h.max(), h.mean()], rtol=1e-6)
+    assert s[6] == 0 and s[7] == 0
 
 
 def test_reference_import_lines_resolve(cuda):
