@@ -49,13 +49,33 @@ __device__ void final_loss_reduce(const float* per_patch, int P, float* total, f
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     double sum = 0.0, sq = 0.0;
     float mn = FLT_MAX, mx = -FLT_MAX;
-    for (int i = tid; i < P; i += blockDim.x) {
-        const float x = __ldcg(per_patch + i);  // written by other CTAs: read through L2
+    auto acc = [&](float x) {
         sum += x;
         sq += static_cast<double>(x) * x;
         mn = fminf(mn, x);
         mx = fmaxf(mx, x);
+    };
+    // This CTA runs alone at the tail of the grid, so its loads are pure latency: issue them as float4 in
+    // batches of 8 independent requests per thread.  (__ldcg: written by other CTAs, read through L2.)
+    int done = 0;
+    if ((reinterpret_cast<uintptr_t>(per_patch) & 15) == 0) {
+        const float4* v4 = reinterpret_cast<const float4*>(per_patch);
+        const int n4 = P >> 2;
+        for (int base = 0; base < n4; base += 8 * blockDim.x) {
+            float4 buf[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * blockDim.x + tid;
+                buf[u] = i < n4 ? __ldcg(v4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (base + u * blockDim.x + tid < n4) acc(buf[u].x), acc(buf[u].y), acc(buf[u].z), acc(buf[u].w);
+            }
+        }
+        done = n4 << 2;
     }
+    for (int i = done + tid; i < P; i += blockDim.x) acc(__ldcg(per_patch + i));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         sum += __shfl_xor_sync(kFull, sum, o);
@@ -155,84 +175,95 @@ __global__ void __launch_bounds__(kCdThreads)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / S, sub = lane % S;
     const int slot = warp * GPW + grp;
-    const int p = (blockIdx.x * kCdWarps + warp) * GPW + grp;
-    const bool live = p < P;
-    const int pc = live ? p : 0;
+    const float inf = __int_as_float(0x7f800000);
 
-    const float* a = xyz1 + static_cast<size_t>(pc) * n * 3;
-    const size_t bpatch = xyz2_index ? static_cast<size_t>(__ldg(xyz2_index + pc)) : static_cast<size_t>(pc);
-    load_patch<S>(s_a[slot], a, n, sub);
-    load_patch<S>(s_b[slot], xyz2 + bpatch * m * 3, m, sub);
-    __syncwarp();
+    // Persistent groups: the grid is sized to one resident wave and every warp strides over the patch list
+    // (all lanes of a warp make the same number of trips; groups past the end idle with `live` false).
+    const int warps_total = gridDim.x * kCdWarps;
+    for (int pw = blockIdx.x * kCdWarps + warp; pw * GPW < P; pw += warps_total) {
+        const int p = pw * GPW + grp;
+        const bool live = p < P;
+        const int pc = live ? p : 0;
+        const float* a = xyz1 + static_cast<size_t>(pc) * n * 3;
+        const size_t bpatch = xyz2_index ? static_cast<size_t>(__ldg(xyz2_index + pc)) : static_cast<size_t>(pc);
+        __syncwarp();  // previous trip's readers are done with the slots
+        load_patch<S>(s_a[slot], a, n, sub);
+        load_patch<S>(s_b[slot], xyz2 + bpatch * m * 3, m, sub);
+        __syncwarp();
 
-    float f1 = 0.0f, f2 = 0.0f, best1 = 0.0f, best2 = 0.0f;
-    int besti1 = 0, besti2 = 0;
-    const float4 pa = s_a[slot][sub < n ? sub : 0], pb = s_b[slot][sub < m ? sub : 0];
-    if (sub < n) {  // direction 1: a_sub against all of b (upstream: x = b - a, strict <)
-#pragma unroll 8
-        for (int j = 0; j < m; ++j) {
-            const float4 q = s_b[slot][j];
-            const float d = sumsq_nvcc(q.x - pa.x, q.y - pa.y, q.z - pa.z);
-            if (j == 0 || d < best1) {
-                best1 = d;
-                besti1 = j;
+        float f1 = 0.0f, f2 = 0.0f, best1 = inf, best2 = inf;
+        int besti1 = 0, besti2 = 0;
+        const float4 pa = s_a[slot][sub < n ? sub : 0], pb = s_b[slot][sub < m ? sub : 0];
+        // One direction: `mine` against the `cnt` points of `other`, two per step with packed FP32x2 math.
+        // Upstream evaluates x = other - mine and keeps the first minimum (strict <), so the pair is
+        // committed in index order.
+        auto nearest = [&](const float4 mine, const float4* other, int cnt, float& best, int& besti) {
+            const float2 mx = make_float2(mine.x, mine.x), my = make_float2(mine.y, mine.y), mz = make_float2(mine.z, mine.z);
+            int j = 0;
+#pragma unroll 4
+            for (; j + 1 < cnt; j += 2) {
+                const float4 q0 = other[j], q1 = other[j + 1];
+                const float2 d = sumsq_nvcc2(sub2(make_float2(q0.x, q1.x), mx), sub2(make_float2(q0.y, q1.y), my),
+                                             sub2(make_float2(q0.z, q1.z), mz));
+                if (d.x < best) best = d.x, besti = j;
+                if (d.y < best) best = d.y, besti = j + 1;
+            }
+            if (j < cnt) {
+                const float4 q = other[j];
+                const float d = sumsq_nvcc(q.x - mine.x, q.y - mine.y, q.z - mine.z);
+                if (d < best) best = d, besti = j;
+            }
+        };
+        if (sub < n) {  // direction 1: a_sub against all of b
+            nearest(pa, s_b[slot], m, best1, besti1);
+            if (live && dist1) dist1[static_cast<size_t>(p) * n + sub] = best1;
+            if (live && idx1) idx1[static_cast<size_t>(p) * n + sub] = besti1;
+            f1 = norm == 1 ? __fsqrt_rn(best1) : best1;
+        }
+        if (sub < m) {  // direction 2: b_sub against all of a
+            nearest(pb, s_a[slot], n, best2, besti2);
+            if (live && dist2) dist2[static_cast<size_t>(p) * m + sub] = best2;
+            if (live && idx2) idx2[static_cast<size_t>(p) * m + sub] = besti2;
+            f2 = norm == 1 ? __fsqrt_rn(best2) : best2;
+        }
+        if (per_patch) {
+            const float s1 = group_sum<S>(f1), s2 = group_sum<S>(f2);
+            if (live && sub == 0) {
+                const float v = s1 / static_cast<float>(n) + s2 / static_cast<float>(m);
+                per_patch[p] = norm == 1 ? 0.5f * v : v;
             }
         }
-        if (live && dist1) dist1[static_cast<size_t>(p) * n + sub] = best1;
-        if (live && idx1) idx1[static_cast<size_t>(p) * n + sub] = besti1;
-        f1 = norm == 1 ? __fsqrt_rn(best1) : best1;
-    }
-    if (sub < m) {  // direction 2: b_sub against all of a
-#pragma unroll 8
-        for (int i = 0; i < n; ++i) {
-            const float4 q = s_a[slot][i];
-            const float d = sumsq_nvcc(q.x - pb.x, q.y - pb.y, q.z - pb.z);
-            if (i == 0 || d < best2) {
-                best2 = d;
-                besti2 = i;
-            }
-        }
-        if (live && dist2) dist2[static_cast<size_t>(p) * m + sub] = best2;
-        if (live && idx2) idx2[static_cast<size_t>(p) * m + sub] = besti2;
-        f2 = norm == 1 ? __fsqrt_rn(best2) : best2;
-    }
-    if (per_patch) {
-        const float s1 = group_sum<S>(f1), s2 = group_sum<S>(f2);
-        if (live && sub == 0) {
-            const float v = s1 / static_cast<float>(n) + s2 / static_cast<float>(m);
-            per_patch[p] = norm == 1 ? 0.5f * v : v;
-        }
-    }
 
-    if (FUSED) {
-        // upstream gradient of the mean reduction: gscale (L2) or gscale * 0.5 / sqrt(d) (L1); g = 2 * that
-        const float u1 = norm == 1 ? __fmul_rn(gscale1, __fdiv_rn(0.5f, f1)) : gscale1;
-        const float u2 = norm == 1 ? __fmul_rn(gscale2, __fdiv_rn(0.5f, f2)) : gscale2;
-        const float g1 = __fmul_rn(u1, 2.0f), g2 = __fmul_rn(u2, 2.0f);
-        if (sub < n) s_g1[slot][sub] = g1;
-        if (sub < m) s_g2[slot][sub] = g2;
-        const unsigned in_a = incoming_mask<S>(sub < m ? besti2 : -1, grp, sub, s_m[warp], lane);  // j's with idx2[j]==sub
-        if (sub < n) {
-            const float4 q = s_b[slot][besti1];
-            float gx = __fmul_rn(g1, pa.x - q.x), gy = __fmul_rn(g1, pa.y - q.y), gz = __fmul_rn(g1, pa.z - q.z);
-            scatter_sub<S>(in_a, s_b[slot], s_g2[slot], pa.x, pa.y, pa.z, gx, gy, gz);
-            if (live) {
-                float* o = gxyz1 + (static_cast<size_t>(p) * n + sub) * 3;
-                o[0] = gx, o[1] = gy, o[2] = gz;
-            }
-        }
-        if (gxyz2) {
-            const unsigned in_b = incoming_mask<S>(sub < n ? besti1 : -1, grp, sub, s_m[warp], lane);
-            if (sub < m) {
-                float gx = 0.f, gy = 0.f, gz = 0.f;
-                scatter_sub<S>(in_b, s_a[slot], s_g1[slot], pb.x, pb.y, pb.z, gx, gy, gz);
-                const float4 q = s_a[slot][besti2];
-                gx = __fadd_rn(gx, __fmul_rn(g2, pb.x - q.x));
-                gy = __fadd_rn(gy, __fmul_rn(g2, pb.y - q.y));
-                gz = __fadd_rn(gz, __fmul_rn(g2, pb.z - q.z));
+        if (FUSED) {
+            // upstream gradient of the mean reduction: gscale (L2) or gscale * 0.5 / sqrt(d) (L1); g = 2 * that
+            const float u1 = norm == 1 ? __fmul_rn(gscale1, __fdiv_rn(0.5f, f1)) : gscale1;
+            const float u2 = norm == 1 ? __fmul_rn(gscale2, __fdiv_rn(0.5f, f2)) : gscale2;
+            const float g1 = __fmul_rn(u1, 2.0f), g2 = __fmul_rn(u2, 2.0f);
+            if (sub < n) s_g1[slot][sub] = g1;
+            if (sub < m) s_g2[slot][sub] = g2;
+            const unsigned in_a = incoming_mask<S>(sub < m ? besti2 : -1, grp, sub, s_m[warp], lane);  // j's with idx2[j]==sub
+            if (sub < n) {
+                const float4 q = s_b[slot][besti1];
+                float gx = __fmul_rn(g1, pa.x - q.x), gy = __fmul_rn(g1, pa.y - q.y), gz = __fmul_rn(g1, pa.z - q.z);
+                scatter_sub<S>(in_a, s_b[slot], s_g2[slot], pa.x, pa.y, pa.z, gx, gy, gz);
                 if (live) {
-                    float* o = gxyz2 + (static_cast<size_t>(p) * m + sub) * 3;
+                    float* o = gxyz1 + (static_cast<size_t>(p) * n + sub) * 3;
                     o[0] = gx, o[1] = gy, o[2] = gz;
+                }
+            }
+            if (gxyz2) {
+                const unsigned in_b = incoming_mask<S>(sub < n ? besti1 : -1, grp, sub, s_m[warp], lane);
+                if (sub < m) {
+                    float gx = 0.f, gy = 0.f, gz = 0.f;
+                    scatter_sub<S>(in_b, s_a[slot], s_g1[slot], pb.x, pb.y, pb.z, gx, gy, gz);
+                    const float4 q = s_a[slot][besti2];
+                    gx = __fadd_rn(gx, __fmul_rn(g2, pb.x - q.x));
+                    gy = __fadd_rn(gy, __fmul_rn(g2, pb.y - q.y));
+                    gz = __fadd_rn(gz, __fmul_rn(g2, pb.z - q.z));
+                    if (live) {
+                        float* o = gxyz2 + (static_cast<size_t>(p) * m + sub) * 3;
+                        o[0] = gx, o[1] = gy, o[2] = gz;
+                    }
                 }
             }
         }
@@ -459,7 +490,20 @@ static int launch_small(const float* xyz1, const float* xyz2, const int32_t* xyz
     const int mx = n > m ? n : m;
     const int S = mx <= 8 ? 8 : (mx <= 16 ? 16 : 32);
     const int per_cta = kCdWarps * (32 / S);
-    const int grid = (P + per_cta - 1) / per_cta;
+    const int need = (P + per_cta - 1) / per_cta;
+    // persistent grid: at most one resident wave (SM count x CTAs per SM for this instantiation)
+    static int wave[3] = {0, 0, 0};
+    const int wi = S == 8 ? 0 : (S == 16 ? 1 : 2);
+    if (wave[wi] == 0) {
+        int dev = 0, sms = 148, per_sm = 4;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (S == 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chamfer_small<8, FUSED>, kCdThreads, 0);
+        else if (S == 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chamfer_small<16, FUSED>, kCdThreads, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chamfer_small<32, FUSED>, kCdThreads, 0);
+        wave[wi] = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const int grid = need < wave[wi] ? need : wave[wi];
 #define GM3D_CD_LAUNCH(SS)                                                                                         \
     chamfer_small<SS, FUSED><<<grid, kCdThreads, 0, st>>>(xyz1, xyz2, xyz2_index, P, n, m, dist1, dist2, idx1, idx2, \
                                                           pp, total, stats, norm, g1, g2, gxyz1, gxyz2, ticket)

@@ -24,6 +24,34 @@ __device__ __forceinline__ float sumsq_acc(float a, float b, float c) {
     return __fmaf_rn(c, c, __fmaf_rn(b, b, __fmul_rn(a, a)));
 }
 
+// ---- packed FP32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2): two independent IEEE round-to-nearest
+// operations per instruction, bit-identical to the scalar forms above.
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; "
+        "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+// two evaluations of sumsq_acc / sumsq_nvcc at once
+__device__ __forceinline__ float2 sumsq_acc2(float2 a, float2 b, float2 c) { return fma2(c, c, fma2(b, b, mul2(a, a))); }
+__device__ __forceinline__ float2 sumsq_nvcc2(float2 a, float2 b, float2 c) { return fma2(c, c, fma2(a, a, mul2(b, b))); }
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 // Order-preserving view of a float as a signed int for values in {-1} U [0, +inf]: non-negative floats

@@ -59,6 +59,7 @@ class GroupLossStep:
         self.ws = e((ws,), torch.uint8) if ws else None
         self.cd_ws = torch.zeros((self.lib.gm3d_workspace_bytes(_lib.OP_CHAMFER_FWD, self.P, k, k, 0),),
                                  dtype=torch.uint8, device=d)  # ticket must start at zero; the kernel re-zeroes it
+        self.side = torch.cuda.Stream(d)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
 
     # algorithmic HBM bytes of one step per cloud (SURVEY App. B formulas; DESIGN.md "Roofline accounting")
@@ -72,16 +73,25 @@ class GroupLossStep:
             "hard_mask": 5 * G + 4 * M,
         }
 
-    def enqueue(self, stream: Optional[int] = None) -> None:
-        """Enqueue the kernels of one step on `stream` (default: torch's current stream)."""
+    def enqueue(self) -> None:
+        """Enqueue the kernels of one step on torch's current stream (+ one forked side stream)."""
         L, p = self.lib, (lambda t: None if t is None else t.data_ptr())
-        st = torch.cuda.current_stream(self.dev).cuda_stream if stream is None else stream
+        main = torch.cuda.current_stream(self.dev)
+        st = main.cuda_stream
         B, N, G, k, P = self.B, self.N, self.G, self.k, self.P
         chk = _lib.check
+        # the mask depends only on loss_pred: fork it onto a side stream so that (also inside a captured
+        # graph) it runs concurrently with FPS, which occupies one SM per cloud and leaves the rest idle
+        fork, join = torch.cuda.Event(), torch.cuda.Event()
+        fork.record(main)
+        self.side.wait_event(fork)
+        chk("gm3d_hard_mask_f32", L.gm3d_hard_mask_f32(p(self.loss_pred), B, G, self.len_keep, self.len_loss, None,
+                                                       self.seed, self.rand_offset, p(self.mask), p(self.patch_index),
+                                                       self.side.cuda_stream))
+        join.record(self.side)
         chk("gm3d_group_f32", L.gm3d_group_f32(p(self.xyz), B, N, G, k, p(self.fps_idx), p(self.center), None,
                                                p(self.neighborhood), None, p(self.ws), st))
-        chk("gm3d_hard_mask_f32", L.gm3d_hard_mask_f32(p(self.loss_pred), B, G, self.len_keep, self.len_loss, None,
-                                                       self.seed, self.rand_offset, p(self.mask), p(self.patch_index), st))
+        main.wait_event(join)
         g = (1.0 if self.norm == 2 else 0.5) / (P * k)  # d mean / d dist (L1: the outer /2 folded in)
         chk("gm3d_chamfer_fused_f32", L.gm3d_chamfer_fused_f32(
             p(self.pred), p(self.neighborhood), p(self.patch_index), P, k, k, g, g, p(self.dist1), p(self.dist2),
@@ -133,11 +143,11 @@ class HostStagedStep(GroupLossStep):
     def d2h_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in (self.h_stats, self.h_per_patch, self.h_mask))
 
-    def enqueue(self, stream: Optional[int] = None) -> None:
+    def enqueue(self) -> None:
         self.xyz.copy_(self.h_xyz, non_blocking=True)
         self.pred.copy_(self.h_pred, non_blocking=True)
         self.loss_pred.copy_(self.h_loss_pred, non_blocking=True)
-        super().enqueue(stream)
+        super().enqueue()
         self.h_stats.copy_(self.stats, non_blocking=True)
         self.h_per_patch.copy_(self.per_patch, non_blocking=True)
         self.h_mask.copy_(self.mask, non_blocking=True)
