@@ -1,0 +1,125 @@
+// Warp-level Chamfer forward + backward of the mean reduction for ONE patch pair with n = m = k <= 32,
+// both patches already in registers (lane l owns prediction point a_l and target point b_l).  Used by the
+// fused per-cloud kernel, where the target patch is the neighbourhood the same warp has just selected.
+//
+// The squared-distance matrix is evaluated once: D[i][j] = |b_j - a_i|^2 is bit-identical to |a_i - b_j|^2
+// (the differences are exact negations, every term is a square), so lane i keeps row i in registers,
+// direction 1 is the in-lane row minimum and direction 2 the column minimum over lanes -- one REDUX.MIN on
+// the (order-preserving) bit pattern per column, the arg-min being the lowest lane of the ballot of the
+// lanes that hold the minimum (= upstream's first minimum).  Only b is staged in shared memory, as point
+// pairs {x0,x1,y0,y1},{z0,z1} so that one LDS.128 + one LDS.64 feed the packed FP32x2 distance of two
+// targets.  Same arithmetic and summation order as chamfer_small<32, true> in chamfer.cu.
+//
+// Replaces, per patch: ChamferFunction.forward/backward + the `.mean()` reductions around it
+// (/root/reference/Point-MAE_SA3D/models/Point_MAE.py:422-426, ..._Classifier_SVM.py:968-982).
+#pragma once
+
+#include "common.cuh"
+
+namespace gm3d {
+
+struct ChamferWarpScratch {  // per warp, 16-byte aligned
+    float4 bxy[16];          // {x_2p, x_2p+1, y_2p, y_2p+1}
+    float2 bz[16];           // {z_2p, z_2p+1}
+    float g2[32];            // 2 * upstream gradient of dist2[j]
+    unsigned in[32];         // incoming-source masks of the backward
+};
+
+struct ChamferWarpOut {
+    float dist1, dist2;  // squared distances of a_lane / b_lane to their nearest neighbour
+    int idx1, idx2;
+    float per_patch;     // valid in every lane
+    float gx, gy, gz;    // d loss / d a_lane
+};
+
+template <int NORM_DYNAMIC = 0>
+__device__ __forceinline__ ChamferWarpOut chamfer_patch_warp(float ax, float ay, float az, float bx, float by, float bz,
+                                                             int k, int norm, float gscale1, float gscale2, int lane,
+                                                             ChamferWarpScratch* __restrict__ sc) {
+    const float inf = __int_as_float(0x7f800000);
+    const bool live = lane < k;
+    // stage b (padding lanes: +inf coordinates => +inf distance, never a minimum)
+    {
+        float* xy = reinterpret_cast<float*>(sc->bxy);
+        float* zz = reinterpret_cast<float*>(sc->bz);
+        const int p = lane >> 1, e = lane & 1;
+        xy[p * 4 + e] = live ? bx : inf;
+        xy[p * 4 + 2 + e] = live ? by : inf;
+        zz[p * 2 + e] = live ? bz : inf;
+    }
+    __syncwarp();
+    const float2 ax2 = make_float2(ax, ax), ay2 = make_float2(ay, ay), az2 = make_float2(az, az);
+    float D[32];
+    float best1 = inf;
+    int besti1 = 0;
+#pragma unroll
+    for (int p = 0; p < 16; ++p) {
+        const float4 xy = sc->bxy[p];
+        const float2 z = sc->bz[p];
+        // upstream evaluates x = other - mine; first minimum wins (strict <), committed in index order
+        const float2 d = sumsq_nvcc2(sub2(make_float2(xy.x, xy.y), ax2), sub2(make_float2(xy.z, xy.w), ay2), sub2(z, az2));
+        D[2 * p] = d.x, D[2 * p + 1] = d.y;
+        if (d.x < best1) best1 = d.x, besti1 = 2 * p;
+        if (d.y < best1) best1 = d.y, besti1 = 2 * p + 1;
+    }
+    // direction 2: column minima over the live lanes
+    float best2 = inf;
+    int besti2 = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const unsigned bits = live ? __float_as_uint(D[j]) : 0xffffffffu;
+        const unsigned mn = __reduce_min_sync(kFull, bits);
+        const unsigned bal = __ballot_sync(kFull, bits == mn);
+        if (lane == j) {
+            best2 = __uint_as_float(mn);
+            besti2 = __ffs(bal) - 1;
+        }
+    }
+    ChamferWarpOut o;
+    o.dist1 = best1, o.dist2 = best2, o.idx1 = besti1, o.idx2 = besti2;
+    const float f1 = live ? (norm == 1 ? __fsqrt_rn(best1) : best1) : 0.0f;
+    const float f2 = live ? (norm == 1 ? __fsqrt_rn(best2) : best2) : 0.0f;
+    float s1 = f1, s2 = f2;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s1 += __shfl_xor_sync(kFull, s1, off);
+        s2 += __shfl_xor_sync(kFull, s2, off);
+    }
+    const float v = s1 / static_cast<float>(k) + s2 / static_cast<float>(k);
+    o.per_patch = norm == 1 ? 0.5f * v : v;
+
+    // backward of the mean: upstream gradient gscale (L2) or gscale * 0.5 / sqrt(d) (L1); g = 2 * that
+    const float u1 = norm == 1 ? __fmul_rn(gscale1, __fdiv_rn(0.5f, f1)) : gscale1;
+    const float u2 = norm == 1 ? __fmul_rn(gscale2, __fdiv_rn(0.5f, f2)) : gscale2;
+    const float g1 = __fmul_rn(u1, 2.0f), g2 = __fmul_rn(u2, 2.0f);
+    sc->g2[lane] = g2;
+    sc->in[lane] = 0u;
+    __syncwarp();
+    // lanes j whose arg-min is point i form a MATCH.ANY group; every member drops the group mask at in[i]
+    const unsigned peers = __match_any_sync(kFull, live ? besti2 : 64 + lane);
+    if (live) sc->in[besti2] = peers;
+    __syncwarp();
+    unsigned sources = sc->in[lane];
+    const float* xy = reinterpret_cast<const float*>(sc->bxy);
+    const float* zz = reinterpret_cast<const float*>(sc->bz);
+    float gx, gy, gz;
+    {
+        const int j = besti1;
+        const float qx = xy[(j >> 1) * 4 + (j & 1)], qy = xy[(j >> 1) * 4 + 2 + (j & 1)], qz = zz[j];
+        gx = __fmul_rn(g1, ax - qx), gy = __fmul_rn(g1, ay - qy), gz = __fmul_rn(g1, az - qz);
+    }
+    while (sources) {  // ascending j: fixed summation order (= the oracle's)
+        const int j = __ffs(sources) - 1;
+        sources &= sources - 1;
+        const float h = sc->g2[j];
+        const float qx = xy[(j >> 1) * 4 + (j & 1)], qy = xy[(j >> 1) * 4 + 2 + (j & 1)], qz = zz[j];
+        gx = __fsub_rn(gx, __fmul_rn(h, qx - ax));
+        gy = __fsub_rn(gy, __fmul_rn(h, qy - ay));
+        gz = __fsub_rn(gz, __fmul_rn(h, qz - az));
+    }
+    o.gx = gx, o.gy = gy, o.gz = gz;
+    __syncwarp();
+    return o;
+}
+
+}  // namespace gm3d

@@ -1,0 +1,372 @@
+// The whole grouping + reconstruction-loss step of one cloud in ONE CTA (sm_100a): every stage of the
+// path is per-cloud work, so a persistent, warp-specialised CTA keeps the cloud in shared memory from the
+// first byte read to the last gradient written and no intermediate ever returns to HBM.
+//
+//   warps 0..7   "sampler": farthest-point sampling.  The cloud arrives by one 1-D bulk copy (TMA engine),
+//                is transposed to structure-of-arrays in shared memory (the layout knn_select.cuh scans),
+//                points + running-min distances live in registers, packed FP32x2 distance updates, one
+//                named barrier per round (the other warps never take part in it).  Each selected centre
+//                is published through s_sel[] the moment it is known.
+//   warps 8..    "workers": pull patch ids g = 0, 1, ... from a shared counter, wait until centre g is
+//                published, select its k nearest points (knn_select.cuh), write the centred neighbourhood,
+//                and -- if patch g is masked -- run Chamfer forward + backward of that patch against the
+//                prediction (chamfer_patch.cuh) while the target patch is still in registers.
+//                One worker first computes the cloud's hard-patch mask (mask_select.cuh).
+//   Sampler warps turn into workers when the last centre is out.  The last CTA to finish reduces the
+//   per-patch losses to the scalar loss + statistics vector (ticket in the workspace).
+//
+// FPS is a chain of G dependent rounds and cannot be made shorter than its latency; everything else
+// (selection, gather, loss, gradients) is throughput work that fits in the issue slots the chain leaves
+// idle on the same SM.  One launch per step, HBM traffic = the compulsory bytes.
+//
+// Replaces, per step, the reference sequence Group.forward -> generate_mask -> forward_loss -> backward:
+// /root/reference/Point-MAE_SA3D/engine_pretrain_Classifier_SVM.py:108-118,157-184;
+// models_mae_learn_loss_Classifier_SVM_feature_besed.py:1238-1260,1062-1109; ..._Classifier_SVM.py:968-982.
+#include <limits.h>
+
+#include "chamfer_patch.cuh"
+#include "knn_select.cuh"
+#include "loss_reduce.cuh"
+#include "mask_select.cuh"
+
+namespace gm3d {
+
+constexpr int kCsFpsWarps = 8;
+constexpr int kCsFpsThreads = kCsFpsWarps * 32;
+
+struct CloudStepParams {
+    const float* xyz;
+    int B, N, G, k;
+    int32_t* fps_idx;
+    float* centers;
+    int64_t* knn_idx;
+    float* nbhd;
+    float* nbhd_org;
+    // loss part (pred == nullptr: grouping only)
+    const float* loss_pred;
+    int len_keep, len_loss;
+    const float* rand_keys;
+    uint64_t seed, offset;
+    uint8_t* mask;
+    int32_t* patch_index;
+    const float* pred;
+    float gscale1, gscale2;
+    int norm;
+    float *dist1, *dist2;
+    int32_t *idx1, *idx2;
+    float *per_patch, *total, *stats, *gxyz1;
+    unsigned* ticket;
+    int use_bulk;
+    int npad;  // SoA length per coordinate: max(1024, N rounded up to 128)
+    int LP;    // G rounded up to a power of two (>= 64)
+};
+
+struct CloudStepSmem {  // offsets into dynamic shared memory
+    size_t sx, sy, sz, aos, sel, cand, patch, cham, key, msel, mrank, total;
+};
+
+__host__ __device__ inline CloudStepSmem cloud_step_layout(int N, int G, int npad, int LP, int warps, bool loss) {
+    CloudStepSmem L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        const size_t at = o;
+        o += (bytes + 15) & ~static_cast<size_t>(15);
+        return at;
+    };
+    L.sx = take(static_cast<size_t>(npad) * 4);
+    L.sy = take(static_cast<size_t>(npad) * 4);
+    L.sz = take(static_cast<size_t>(npad) * 4);
+    L.aos = take(static_cast<size_t>((N + 3) & ~3) * 12);
+    L.sel = take(static_cast<size_t>(G) * 4);
+    L.cand = take(static_cast<size_t>(warps) * 64 * 8);
+    L.patch = take(static_cast<size_t>(warps) * 96 * 4);
+    L.cham = loss ? take(static_cast<size_t>(warps) * sizeof(ChamferWarpScratch)) : 0;
+    L.key = (loss && LP > 64) ? take(static_cast<size_t>(LP) * 8) : 0;
+    L.msel = loss ? take(static_cast<size_t>(LP)) : 0;
+    L.mrank = loss ? take(static_cast<size_t>(G) * 2) : 0;
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ void fps_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kCsFpsThreads) : "memory"); }
+__device__ __forceinline__ int ld_volatile_s32(const int* p) {
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_s32(int* p, int v) {
+    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+template <int PPT, int WARPS, bool LOSS>
+__global__ void __launch_bounds__(WARPS * 32, 1) cloud_step_kernel(const __grid_constant__ CloudStepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int2 s_red[2][kCsFpsWarps];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_next;        // next patch id to hand out
+    __shared__ int s_mask_ready;  // 1 once s_msel / s_mrank are valid
+
+    const int N = p.N, G = p.G, k = p.k;
+    const CloudStepSmem L = cloud_step_layout(N, G, p.npad, p.LP, WARPS, LOSS);
+    float* sx = reinterpret_cast<float*>(smem_raw + L.sx);
+    float* sy = reinterpret_cast<float*>(smem_raw + L.sy);
+    float* sz = reinterpret_cast<float*>(smem_raw + L.sz);
+    float* s_aos = reinterpret_cast<float*>(smem_raw + L.aos);
+    int* s_sel = reinterpret_cast<int*>(smem_raw + L.sel);
+    uint8_t* s_msel = reinterpret_cast<uint8_t*>(smem_raw + L.msel);
+    short* s_mrank = reinterpret_cast<short*>(smem_raw + L.mrank);
+
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* cloud = p.xyz + static_cast<size_t>(b) * N * 3;
+    const int M = G - p.len_keep;
+
+    // ---------------- prologue: cloud -> shared memory (AoS landing zone -> SoA), flags
+    if (p.use_bulk) {
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_fence_init();
+        }
+    }
+    for (int g = tid; g < G; g += WARPS * 32) s_sel[g] = g == 0 ? 0 : -1;  // FPS starts at point 0
+    if (tid == 0) s_next = 0, s_mask_ready = 0;
+    __syncthreads();
+    if (p.use_bulk) {
+        if (tid == 0) {
+            const uint32_t bytes = static_cast<uint32_t>(N) * 12u;
+            mbar_arrive_expect_tx(&s_bar, bytes);
+            bulk_g2s(s_aos, cloud, bytes, &s_bar);
+        }
+    }
+
+    float2 X[PPT / 2], Y[PPT / 2], Z[PPT / 2], T[PPT / 2];
+    if (warp < kCsFpsWarps) {
+        if (p.use_bulk) mbar_wait(&s_bar, 0);
+        const float* src = p.use_bulk ? s_aos : cloud;
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) {
+            const int i = s * kCsFpsThreads + tid;
+            float x = 0.f, y = 0.f, z = 0.f, t = -1.0f;  // min(d, -1) stays -1: a slot past N is never selected
+            if (i < N) {
+                x = src[3 * i + 0], y = src[3 * i + 1], z = src[3 * i + 2];
+                sx[i] = x, sy[i] = y, sz[i] = z;
+                // pointnet2: `if (mag <= 1e-3) continue;` with a double literal => double compare
+                t = (static_cast<double>(sumsq_nvcc(x, y, z)) <= 1e-3) ? -1.0f : 1e10f;
+            }
+            if (s & 1) X[s >> 1].y = x, Y[s >> 1].y = y, Z[s >> 1].y = z, T[s >> 1].y = t;
+            else X[s >> 1].x = x, Y[s >> 1].x = y, Z[s >> 1].x = z, T[s >> 1].x = t;
+        }
+        const float inf = __uint_as_float(kInfBits);
+        for (int i = N + tid; i < p.npad; i += kCsFpsThreads) sx[i] = inf, sy[i] = inf, sz[i] = inf;
+    }
+    __syncthreads();  // SoA cloud visible to every warp
+
+    if (warp < kCsFpsWarps) {
+        // ---------------- sampler: G - 1 dependent rounds
+        int old = 0;
+        for (int j = 1; j < G; ++j) {
+            const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
+            const float2 x2 = make_float2(x1, x1), y2 = make_float2(y1, y1), z2 = make_float2(z1, z1);
+            float m[PPT];
+#pragma unroll
+            for (int h = 0; h < PPT / 2; ++h) {
+                const float2 d = sumsq_nvcc2(sub2(X[h], x2), sub2(Y[h], y2), sub2(Z[h], z2));
+                T[h].x = fminf(d.x, T[h].x);
+                T[h].y = fminf(d.y, T[h].y);
+                m[2 * h] = T[h].x, m[2 * h + 1] = T[h].y;
+            }
+            // thread arg-max, lowest slot on ties (slot s <-> point s * 256 + tid): pairwise tournament
+            int mi[PPT];
+#pragma unroll
+            for (int s = 0; s < PPT; ++s) mi[s] = s;
+#pragma unroll
+            for (int w = 1; w < PPT; w <<= 1) {
+#pragma unroll
+                for (int s = 0; s < PPT; s += 2 * w) {
+                    const bool hi = m[s + w] > m[s];
+                    m[s] = hi ? m[s + w] : m[s];
+                    mi[s] = hi ? mi[s + w] : mi[s];
+                }
+            }
+            const int v = f2ord(m[0]);
+            const int besti = mi[0] * kCsFpsThreads + tid;
+            const int vmax = __reduce_max_sync(kFull, v);
+            const int kmin = __reduce_min_sync(kFull, v == vmax ? besti : INT_MAX);
+            if (lane == 0) s_red[j & 1][warp] = make_int2(vmax, kmin);
+            fps_bar();
+            const int2 r = lane < kCsFpsWarps ? s_red[j & 1][lane] : make_int2(INT_MIN, INT_MAX);
+            const int gmax = __reduce_max_sync(kFull, r.x);
+            old = __reduce_min_sync(kFull, r.x == gmax ? r.y : INT_MAX);
+            if (tid == 0) st_volatile_s32(&s_sel[j], old);  // publishes centre j to the workers
+        }
+        fps_bar();
+        for (int g = tid; g < G; g += kCsFpsThreads) {
+            const int i = s_sel[g];
+            p.fps_idx[static_cast<size_t>(b) * G + g] = i;
+            float* c = p.centers + (static_cast<size_t>(b) * G + g) * 3;
+            c[0] = sx[i], c[1] = sy[i], c[2] = sz[i];
+        }
+    } else if (LOSS && warp == WARPS - 1) {
+        // ---------------- the cloud's hard-patch mask (needs loss_pred only), then the masked rank of each patch
+        const float* lrow = p.loss_pred ? p.loss_pred + static_cast<size_t>(b) * G : nullptr;
+        const float* rrow = p.rand_keys ? p.rand_keys + static_cast<size_t>(b) * G : nullptr;
+        uint8_t* mrow = p.mask + static_cast<size_t>(b) * G;
+        int32_t* prow = p.patch_index ? p.patch_index + static_cast<size_t>(b) * M : nullptr;
+        const uint64_t ctr = p.offset + static_cast<uint64_t>(b) * G;
+        if (p.LP <= 64) {
+            hard_mask_row_warp64(lrow, G, p.len_keep, p.len_loss, rrow, p.seed, ctr, b, mrow, prow, s_msel, lane);
+        } else {
+            hard_mask_row(lrow, G, p.LP, p.len_keep, p.len_loss, rrow, p.seed, ctr, b, mrow, prow,
+                          reinterpret_cast<unsigned long long*>(smem_raw + L.key), s_msel, lane, 32, SyncWarp());
+        }
+        __syncwarp();
+        int base = 0;
+        for (int c0 = 0; c0 < G; c0 += 32) {
+            const int g = c0 + lane;
+            const bool sel = g < G && s_msel[g];
+            const unsigned bal = __ballot_sync(kFull, sel);
+            if (g < G) s_mrank[g] = sel ? static_cast<short>(base + __popc(bal & ((1u << lane) - 1u))) : static_cast<short>(-1);
+            base += __popc(bal);
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) st_volatile_s32(&s_mask_ready, 1);
+    }
+
+    // ---------------- workers: one patch per trip
+    u64* cb = reinterpret_cast<u64*>(smem_raw + L.cand) + warp * 64;
+    float* s_patch = reinterpret_cast<float*>(smem_raw + L.patch) + warp * 96;
+    ChamferWarpScratch* csc = LOSS ? reinterpret_cast<ChamferWarpScratch*>(smem_raw + L.cham) + warp : nullptr;
+    for (;;) {
+        int g = 0;
+        if (lane == 0) g = atomicAdd(&s_next, 1);
+        g = __shfl_sync(kFull, g, 0);
+        if (g >= G) break;
+        int c;
+        while ((c = ld_volatile_s32(&s_sel[g])) < 0) __nanosleep(40);
+        const float qx = sx[c], qy = sy[c], qz = sz[c];
+
+        KnnStream<1> st;
+        st.qx[0] = qx, st.qy[0] = qy, st.qz[0] = qz;
+        st.cnt[0] = 0;
+        if (!bootstrap_query(sx, sy, sz, 0, qx, qy, qz, k, lane, cb, st.top[0], st.thr[0])) {
+            st.thr[0] = __uint_as_float(kFltMaxBits);
+            st.top[0] = kKeyInf;
+            stream_tile<1>(st, sx, sy, sz, 0, min(N, kKnnTile), k, lane, cb);
+        }
+        if (N > kKnnTile) stream_tile<1>(st, sx + kKnnTile, sy + kKnnTile, sz + kKnnTile, kKnnTile, N - kKnnTile, k, lane, cb);
+        knn_finish<1>(st, 0, cb, lane);
+
+        // gather + centre-normalise; lane l < k owns neighbour l
+        const unsigned pi = lane < k ? static_cast<unsigned>(st.top[0] & 0xffffffffu) : 0u;
+        const float ox = sx[pi], oy = sy[pi], oz = sz[pi];
+        const float bx = __fsub_rn(ox, qx), by = __fsub_rn(oy, qy), bz = __fsub_rn(oz, qz);
+        const size_t row = (static_cast<size_t>(b) * G + g) * k;
+        if (p.knn_idx && lane < k) p.knn_idx[row + lane] = static_cast<int64_t>(pi);
+        const int nf = 3 * k;  // floats per patch
+        if (p.nbhd_org) {
+            __syncwarp();
+            if (lane < k) s_patch[3 * lane] = ox, s_patch[3 * lane + 1] = oy, s_patch[3 * lane + 2] = oz;
+            __syncwarp();
+            for (int t = lane; t < nf; t += 32) p.nbhd_org[row * 3 + t] = s_patch[t];
+        }
+        __syncwarp();
+        if (lane < k) s_patch[3 * lane] = bx, s_patch[3 * lane + 1] = by, s_patch[3 * lane + 2] = bz;
+        __syncwarp();
+        for (int t = lane; t < nf; t += 32) p.nbhd[row * 3 + t] = s_patch[t];
+
+        if (LOSS) {
+            while (ld_volatile_s32(&s_mask_ready) == 0) __nanosleep(40);
+            const int mr = s_mrank[g];
+            if (mr >= 0) {  // warp-uniform
+                const size_t pp = static_cast<size_t>(b) * M + mr;
+                const float* pa = p.pred + pp * nf;
+                __syncwarp();
+                for (int t = lane; t < nf; t += 32) s_patch[t] = __ldg(pa + t);
+                __syncwarp();
+                const int ls = lane < k ? lane : 0;
+                const float ax = s_patch[3 * ls], ay = s_patch[3 * ls + 1], az = s_patch[3 * ls + 2];
+                const ChamferWarpOut o = chamfer_patch_warp(ax, ay, az, bx, by, bz, k, p.norm, p.gscale1, p.gscale2, lane, csc);
+                if (lane < k) {
+                    if (p.dist1) p.dist1[pp * k + lane] = o.dist1;
+                    if (p.dist2) p.dist2[pp * k + lane] = o.dist2;
+                    if (p.idx1) p.idx1[pp * k + lane] = o.idx1;
+                    if (p.idx2) p.idx2[pp * k + lane] = o.idx2;
+                    s_patch[3 * lane] = o.gx, s_patch[3 * lane + 1] = o.gy, s_patch[3 * lane + 2] = o.gz;
+                }
+                if (lane == 0 && p.per_patch) p.per_patch[pp] = o.per_patch;
+                __syncwarp();
+                for (int t = lane; t < nf; t += 32) p.gxyz1[pp * nf + t] = s_patch[t];
+            }
+        }
+    }
+
+    if (LOSS && p.ticket) {
+        if (last_cta(p.ticket)) final_loss_reduce(p.per_patch, p.B * M, p.total, p.stats);
+    }
+}
+
+size_t cloud_step_workspace_bytes(int P) { return P > 0 ? 16 + static_cast<size_t>(P) * sizeof(float) : 0; }
+
+template <int PPT, int WARPS, bool LOSS>
+static int launch_cloud_step(const CloudStepParams& p, size_t smem, cudaStream_t st) {
+    auto kern = cloud_step_kernel<PPT, WARPS, LOSS>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    kern<<<p.B, WARPS * 32, smem, st>>>(p);
+    return launch_status();
+}
+
+constexpr int kCsWarps = 24;  // 8 sampler + 16 worker warps
+
+// Largest N the fused kernel serves: 8 points per sampler thread.
+constexpr int kCloudStepMaxN = kCsFpsThreads * 8;
+
+bool cloud_step_supported(int N, int G, int k) { return N <= kCloudStepMaxN && G <= 1024 && k <= 32 && N >= 1 && G <= N; }
+
+int cloud_step_launch(CloudStepParams p, cudaStream_t st) {
+    const bool loss = p.pred != nullptr;
+    p.npad = p.N <= kKnnTile ? kKnnTile : ((p.N + 127) & ~127);
+    int LP = 64;
+    while (LP < p.G) LP <<= 1;
+    p.LP = LP;
+    p.use_bulk = (p.N % 4 == 0) && (reinterpret_cast<uintptr_t>(p.xyz) % 16 == 0);
+    const CloudStepSmem L = cloud_step_layout(p.N, p.G, p.npad, p.LP, kCsWarps, loss);
+    if (L.total > 200 * 1024) return GM3D_ENOSUP;
+    if (p.N <= kCsFpsThreads * 4) {
+        return loss ? launch_cloud_step<4, kCsWarps, true>(p, L.total, st) : launch_cloud_step<4, kCsWarps, false>(p, L.total, st);
+    }
+    return loss ? launch_cloud_step<8, kCsWarps, true>(p, L.total, st) : launch_cloud_step<8, kCsWarps, false>(p, L.total, st);
+}
+
+}  // namespace gm3d
+
+GM3D_API int gm3d_cloud_step_f32(const float* xyz, int B, int N, int G, int k, int32_t* fps_idx, float* centers,
+                                 int64_t* knn_idx, float* nbhd, float* nbhd_org, const float* loss_pred, int len_keep,
+                                 int len_loss, const float* rand_keys, uint64_t seed, uint64_t offset, uint8_t* mask,
+                                 int32_t* patch_index, const float* pred, float gscale1, float gscale2, int norm,
+                                 float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, float* per_patch, float* total,
+                                 float* stats, float* gxyz1, void* ws, void* stream) {
+    using namespace gm3d;
+    if (!xyz || !fps_idx || !centers || !nbhd || B <= 0 || N <= 0 || G <= 0 || k <= 0 || k > N || G > N) return GM3D_EINVAL;
+    if (!cloud_step_supported(N, G, k)) return GM3D_ENOSUP;
+    CloudStepParams p{};
+    p.xyz = xyz, p.B = B, p.N = N, p.G = G, p.k = k;
+    p.fps_idx = fps_idx, p.centers = centers, p.knn_idx = knn_idx, p.nbhd = nbhd, p.nbhd_org = nbhd_org;
+    if (pred) {
+        if (!mask || !gxyz1 || len_keep < 0 || len_keep >= G || len_loss < 0 || len_loss > G - len_keep) return GM3D_EINVAL;
+        if (len_loss > 0 && !loss_pred) return GM3D_EINVAL;
+        if (norm != 1 && norm != 2) return GM3D_EINVAL;
+        const bool reduce = total || stats;
+        if (reduce && !ws) return GM3D_EINVAL;
+        p.loss_pred = loss_pred, p.len_keep = len_keep, p.len_loss = len_loss, p.rand_keys = rand_keys;
+        p.seed = seed, p.offset = offset, p.mask = mask, p.patch_index = patch_index;
+        p.pred = pred, p.gscale1 = gscale1, p.gscale2 = gscale2, p.norm = norm;
+        p.dist1 = dist1, p.dist2 = dist2, p.idx1 = idx1, p.idx2 = idx2;
+        p.per_patch = per_patch ? per_patch : (reduce ? reinterpret_cast<float*>(static_cast<char*>(ws) + 16) : nullptr);
+        p.total = total, p.stats = stats, p.gxyz1 = gxyz1;
+        p.ticket = reduce ? static_cast<unsigned*>(ws) : nullptr;
+    }
+    return cloud_step_launch(p, as_stream(stream));
+}

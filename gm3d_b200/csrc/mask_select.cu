@@ -5,7 +5,7 @@
 // Reference call sites (/root/reference/Point-MAE_SA3D): utils/miscc.py:19 (gather_operation);
 // ..._feature_besed.py:1062-1109 and models/Point_MAE.py:297-320 (masks); models/Point_MAE.py:425 and
 // ..._Classifier_SVM.py:972 (`neighborhood[mask]`).
-#include "common.cuh"
+#include "mask_select.cuh"
 
 namespace gm3d {
 
@@ -44,56 +44,8 @@ __global__ void __launch_bounds__(256)
     if (n < N) gfeat[(static_cast<size_t>(b) * C + c) * N + n] = acc;
 }
 
-// ---------------------------------------------------------------- Philox4x32-10
-__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-    c[0] = n0, c[1] = n1, c[2] = n2, c[3] = n3;
-}
-// uniform in [0,1) with 24 random bits, from Philox4x32-10(key = seed, counter = ctr)
-__device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t ctr) {
-    uint32_t c[4] = {static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), 0u, 0u};
-    uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        philox_round(c, k0, k1);
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    return static_cast<float>(c[0] >> 8) * (1.0f / 16777216.0f);
-}
-
 // ---------------------------------------------------------------- hard-patch mask (+ masked-patch index list)
-// Order-preserving map float -> uint32 (total order of the finite floats, -0 < +0).
-__device__ __forceinline__ unsigned ord_bits(float f) {
-    const unsigned u = __float_as_uint(__fadd_rn(f, 0.0f));  // -0 -> +0 so that equal values get equal bits
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
-// Ascending bitonic sort of LP (power of two) 64-bit keys in shared memory by the whole CTA.
-__device__ void smem_bitonic_sort(unsigned long long* key, int LP) {
-    for (int sz = 2; sz <= LP; sz <<= 1) {
-        for (int st = sz >> 1; st > 0; st >>= 1) {
-            for (int t = threadIdx.x; t < LP / 2; t += blockDim.x) {
-                const int i = ((t / st) * (st << 1)) + (t % st);
-                const int j = i + st;
-                const bool up = (i & sz) == 0;
-                const unsigned long long a = key[i], c = key[j];
-                if ((a > c) == up) {
-                    key[i] = c;
-                    key[j] = a;
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
-// One CTA per row.  Keys are (ordered value bits << 32 | index): ascending key order == stable ascending
-// value order, so "the len_loss largest, ties -> higher index larger" is the tail of the sorted array.
-// Pass 1 selects the top len_loss by loss_pred, pass 2 the top n_rand by random key among the rest; then
-// the row's mask is written and (optionally) compacted in order into patch_index.
+// One CTA per row (mask_select.cuh does the work).
 __global__ void __launch_bounds__(1024)
     hard_mask_kernel(const float* __restrict__ loss_pred, int L, int LP, int len_keep, int len_loss,
                      const float* __restrict__ rand_keys, uint64_t seed, uint64_t offset, uint8_t* __restrict__ mask,
@@ -101,48 +53,12 @@ __global__ void __launch_bounds__(1024)
     extern __shared__ __align__(8) unsigned char smem_raw[];
     unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw);
     uint8_t* s_sel = reinterpret_cast<uint8_t*>(s_key + LP);
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const int n_rand = L - len_keep - len_loss;
+    const int b = blockIdx.x;
     const int M = L - len_keep;
-
-    for (int i = tid; i < LP; i += blockDim.x) {
-        s_sel[i] = 0;
-        s_key[i] = (i < L && len_loss > 0)
-                       ? (static_cast<unsigned long long>(ord_bits(__ldg(loss_pred + static_cast<size_t>(b) * L + i))) << 32) | static_cast<unsigned>(i)
-                       : 0ull;  // pads sort to the front
-    }
-    __syncthreads();
-    if (len_loss > 0) {
-        smem_bitonic_sort(s_key, LP);
-        for (int t = tid; t < len_loss; t += blockDim.x) s_sel[static_cast<unsigned>(s_key[LP - 1 - t] & 0xffffffffu)] = 1;
-        __syncthreads();
-    }
-    if (n_rand > 0) {
-        for (int i = tid; i < LP; i += blockDim.x) {
-            unsigned long long kkey = 0ull;  // pads and already-selected patches sort to the front
-            if (i < L && !s_sel[i]) {
-                const float r = rand_keys ? __ldg(rand_keys + static_cast<size_t>(b) * L + i)
-                                          : philox_uniform(seed, offset + static_cast<uint64_t>(b) * L + i);
-                kkey = (static_cast<unsigned long long>(ord_bits(r)) << 32) | static_cast<unsigned>(i);
-            }
-            s_key[i] = kkey;
-        }
-        __syncthreads();
-        smem_bitonic_sort(s_key, LP);
-        for (int t = tid; t < n_rand; t += blockDim.x) s_sel[static_cast<unsigned>(s_key[LP - 1 - t] & 0xffffffffu)] = 1;
-        __syncthreads();
-    }
-    for (int i = tid; i < L; i += blockDim.x) mask[static_cast<size_t>(b) * L + i] = s_sel[i];
-    if (patch_index && tid < 32) {  // ordered compaction by warp 0
-        int base = 0;
-        for (int c0 = 0; c0 < L; c0 += 32) {
-            const int i = c0 + tid;
-            const bool sel = i < L && s_sel[i];
-            const unsigned bal = __ballot_sync(kFull, sel);
-            if (sel) patch_index[static_cast<size_t>(b) * M + base + __popc(bal & ((1u << tid) - 1u))] = b * L + i;
-            base += __popc(bal);
-        }
-    }
+    hard_mask_row(loss_pred ? loss_pred + static_cast<size_t>(b) * L : nullptr, L, LP, len_keep, len_loss,
+                  rand_keys ? rand_keys + static_cast<size_t>(b) * L : nullptr, seed, offset + static_cast<uint64_t>(b) * L, b,
+                  mask + static_cast<size_t>(b) * L, patch_index ? patch_index + static_cast<size_t>(b) * M : nullptr, s_key,
+                  s_sel, threadIdx.x, blockDim.x, SyncCta());
 }
 
 // ---------------------------------------------------------------- boolean-mask patch select

@@ -20,14 +20,20 @@ import torch
 from . import _lib
 from .masking import mask_lengths
 
-KERNELS_PER_STEP = 4  # fps, knn_group, hard_mask (+patch index), chamfer fused (fwd + bwd + loss reduction)
+KERNELS_PER_STEP = 4  # unfused: fps, knn_group, hard_mask (+patch index), chamfer fused (fwd + bwd + loss reduction)
+FUSED_MAX_N, FUSED_MAX_G = 2048, 1024  # gm3d_cloud_step_f32 serves these; larger clouds use the 4-kernel sequence
 
 
 class GroupLossStep:
     def __init__(self, B: int, N: int, G: int, k: int, mask_ratio: float = 0.6, epoch: int = 199,
                  total_epoch: int = 400, ratio_cap: float = 0.8, norm: int = 2, device=None, seed: int = 0,
-                 rand_offset: int = 0):
+                 rand_offset: int = 0, fused: Optional[bool] = None):
         self.lib = _lib.load()
+        can_fuse = N <= FUSED_MAX_N and G <= FUSED_MAX_G and k <= _lib.KNN_MAX_K
+        if fused and not can_fuse:
+            raise NotImplementedError(f"gm3d_cloud_step_f32 serves N <= {FUSED_MAX_N}, G <= {FUSED_MAX_G}")
+        self.fused = can_fuse if fused is None else fused
+        self.kernels_per_step = 1 if self.fused else KERNELS_PER_STEP
         self.dev = torch.device(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
         if self.dev.type != "cuda":
             raise RuntimeError("GroupLossStep runs on CUDA only (gm3d_b200 has no CPU fallback)")
@@ -57,7 +63,8 @@ class GroupLossStep:
         self.status = torch.zeros((1,), dtype=i32, device=d)
         ws = self.lib.gm3d_workspace_bytes(_lib.OP_GROUP, B, N, G, k)
         self.ws = e((ws,), torch.uint8) if ws else None
-        self.cd_ws = torch.zeros((self.lib.gm3d_workspace_bytes(_lib.OP_CHAMFER_FWD, self.P, k, k, 0),),
+        self.cd_ws = torch.zeros((max(self.lib.gm3d_workspace_bytes(_lib.OP_CHAMFER_FWD, self.P, k, k, 0),
+                                      self.lib.gm3d_workspace_bytes(_lib.OP_CLOUD_STEP, self.P, 0, 0, 0)),),
                                  dtype=torch.uint8, device=d)  # ticket must start at zero; the kernel re-zeroes it
         self.side = torch.cuda.Stream(d)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -80,6 +87,14 @@ class GroupLossStep:
         st = main.cuda_stream
         B, N, G, k, P = self.B, self.N, self.G, self.k, self.P
         chk = _lib.check
+        g = (1.0 if self.norm == 2 else 0.5) / (P * k)  # d mean / d dist (L1: the outer /2 folded in)
+        if self.fused:  # the whole step in one launch, one CTA per cloud
+            chk("gm3d_cloud_step_f32", L.gm3d_cloud_step_f32(
+                p(self.xyz), B, N, G, k, p(self.fps_idx), p(self.center), None, p(self.neighborhood), None,
+                p(self.loss_pred), self.len_keep, self.len_loss, None, self.seed, self.rand_offset, p(self.mask),
+                p(self.patch_index), p(self.pred), g, g, self.norm, p(self.dist1), p(self.dist2), p(self.idx1),
+                p(self.idx2), p(self.per_patch), p(self.total), p(self.stats), p(self.grad_pred), p(self.cd_ws), st))
+            return
         # the mask depends only on loss_pred: fork it onto a side stream so that (also inside a captured
         # graph) it runs concurrently with FPS, which occupies one SM per cloud and leaves the rest idle
         fork, join = torch.cuda.Event(), torch.cuda.Event()
@@ -92,7 +107,6 @@ class GroupLossStep:
         chk("gm3d_group_f32", L.gm3d_group_f32(p(self.xyz), B, N, G, k, p(self.fps_idx), p(self.center), None,
                                                p(self.neighborhood), None, p(self.ws), st))
         main.wait_event(join)
-        g = (1.0 if self.norm == 2 else 0.5) / (P * k)  # d mean / d dist (L1: the outer /2 folded in)
         chk("gm3d_chamfer_fused_f32", L.gm3d_chamfer_fused_f32(
             p(self.pred), p(self.neighborhood), p(self.patch_index), P, k, k, g, g, p(self.dist1), p(self.dist2),
             p(self.idx1), p(self.idx2), p(self.per_patch), p(self.total), p(self.stats), self.norm, p(self.grad_pred),

@@ -24,6 +24,8 @@
  *                                                                   models/Point_MAE.py:297-320
  *   gm3d_loss_stats_f32     the scalars fed to misc.all_reduce_mean util/misc.py:345-353,
  *                                                                   engine_pretrain_Classifier_SVM.py:297-305
+ *   gm3d_cloud_step_f32     one pre-training step of the path in one launch: Group.forward ->
+ *                           generate_mask -> forward_loss -> backward   engine_pretrain_Classifier_SVM.py:108-118,157-184
  *
  * Conventions
  *   - Every pointer is a DEVICE pointer on the current CUDA device unless marked HOST.  Tensors are
@@ -49,7 +51,7 @@
 extern "C" {
 #endif
 
-#define GM3D_ABI_VERSION 1
+#define GM3D_ABI_VERSION 2
 
 #define GM3D_OK 0
 #define GM3D_EINVAL (-1)  /* bad shape: B/N/G/k <= 0, k > N, G > N, NULL required pointer ...        */
@@ -63,6 +65,7 @@ extern "C" {
 #define GM3D_OP_CHAMFER_BWD 5
 #define GM3D_OP_HARD_MASK 6
 #define GM3D_OP_LOSS_STATS 7
+#define GM3D_OP_CLOUD_STEP 8
 
 /* Largest k gm3d_knn_f32 / gm3d_group_f32 accept (one warp holds the sorted k-list, one entry per lane). */
 #define GM3D_KNN_MAX_K 32
@@ -164,6 +167,24 @@ int gm3d_hard_mask_f32(const float* loss_pred /* may be NULL iff len_loss == 0 *
 /* Per-rank loss statistics for the one small all-reduce of a step.  per_patch (P) ->
  * stats[GM3D_LOSS_STATS_LEN] = { sum, sum of squares, count, min, max, mean, 0, 0 } (deterministic). */
 int gm3d_loss_stats_f32(const float* per_patch, int P, float* stats, void* stream);
+
+/* The whole step of the path in ONE launch, one CTA per cloud (N <= 2048, G <= 1024, k <= 32, else
+ * GM3D_ENOSUP -- use the separate entry points): farthest-point sampling, kNN patches + centre-normalisation,
+ * hard-patch mask, and Chamfer forward + backward of the mean-reduced loss between pred and the MASKED
+ * target patches `nbhd[mask]`.  Outputs are exactly those of gm3d_group_f32, gm3d_hard_mask_f32 and
+ * gm3d_chamfer_fused_f32(xyz1 = pred, xyz2 = nbhd, xyz2_index = patch_index, n = m = k) run in sequence
+ * (bit-identical indices; same arithmetic and summation order for the loss and gradients).
+ *   pred (B*M, k, 3) with M = G - len_keep; pred == NULL => grouping only (everything after nbhd_org ignored).
+ *   ws: gm3d_workspace_bytes(GM3D_OP_CLOUD_STEP, B*M, 0, 0, 0) bytes, first 16 zero before the first launch
+ *   (needed for total / stats; same ticket protocol as gm3d_chamfer_fwd_f32). */
+int gm3d_cloud_step_f32(const float* xyz, int B, int N, int G, int k, int32_t* fps_idx, float* centers,
+                        int64_t* knn_idx /* or NULL */, float* nbhd, float* nbhd_org /* or NULL */,
+                        const float* loss_pred /* (B,G); may be NULL iff len_loss == 0 */, int len_keep, int len_loss,
+                        const float* rand_keys /* or NULL => Philox */, uint64_t seed, uint64_t offset,
+                        uint8_t* mask /* (B,G) */, int32_t* patch_index /* (B*M) or NULL */, const float* pred,
+                        float gscale1, float gscale2, int norm /* 1|2 */, float* dist1, float* dist2, int32_t* idx1,
+                        int32_t* idx2, float* per_patch, float* total, float* stats, float* gxyz1 /* (B*M,k,3) */,
+                        void* ws, void* stream);
 
 #ifdef __cplusplus
 }

@@ -472,3 +472,75 @@ def test_reference_import_lines_resolve(cuda):
     _, I = KNN(4, transpose_mode=True)(xyz, ctr)
     assert tuple(I.shape) == (2, 8, 4)
     assert ChamferDistanceL2()(xyz, xyz).item() == 0
+
+
+# ------------------------------------------------------------------------------------------ fused per-cloud step
+@pytest.mark.parametrize("kind", ["ball", "sphere"])
+@pytest.mark.parametrize("B,N,G,k,ratio,norm", [
+    (8, 1024, 64, 32, 0.6, 2),      # BASELINE config[0] / config[1] shape
+    (5, 2048, 128, 32, 0.6, 2),     # two tiles: bootstrap + streamed tile
+    (3, 777, 50, 16, 0.6, 1),       # ragged N (no bulk copy), k < 32, L1
+    (4, 512, 256, 8, 0.8, 2),       # M2AE level: mask over 256 patches (shared-memory sort path)
+    (2, 2048, 512, 16, 0.8, 2),     # M2AE level 0
+    (6, 96, 40, 32, 0.5, 2),        # tiny cloud: bootstrap overflows, streaming fallback
+])
+def test_cloud_step_fused_equals_kernel_sequence_and_oracle(cuda, kind, B, N, G, k, ratio, norm):
+    """gm3d_cloud_step_f32 (one launch, one CTA per cloud) against the four-kernel sequence (bit-identical
+    on every output) and against the CPU oracle (indices exact, loss / gradients within 1e-5)."""
+    from gm3d_b200.pipeline import GroupLossStep
+    x = synthetic_clouds(B, N, 77 + N + G, kind)
+    rng = np.random.default_rng(5)
+    steps = [GroupLossStep(B, N, G, k, ratio, device=cuda, seed=11, rand_offset=3, norm=norm, fused=f) for f in (True, False)]
+    M = steps[0].M
+    lp = rng.standard_normal((B, G)).astype(np.float32)
+    pred = (rng.standard_normal((B * M, k, 3)) * 0.08).astype(np.float32)
+    for s in steps:
+        s.xyz.copy_(dev(x, cuda)); s.loss_pred.copy_(dev(lp, cuda)); s.pred.copy_(dev(pred, cuda))
+        for t in (s.fps_idx, s.center, s.neighborhood, s.mask, s.patch_index, s.dist1, s.dist2, s.idx1, s.idx2,
+                  s.per_patch, s.total, s.grad_pred, s.stats):
+            t.fill_(0)  # outputs must be fully written by the step itself
+        s.run()
+    torch.cuda.synchronize()
+    f, u = steps
+    assert f.kernels_per_step == 1 and u.kernels_per_step == 4
+    for name in ("fps_idx", "center", "neighborhood", "mask", "patch_index", "dist1", "dist2", "idx1", "idx2",
+                 "per_patch", "total", "stats", "grad_pred"):
+        assert np.array_equal(host(getattr(f, name)), host(getattr(u, name))), name
+    # oracle
+    w = co.group(x, G, k)
+    assert np.array_equal(host(f.fps_idx), w["fps_idx"])
+    assert np.array_equal(host(f.center), w["center"])
+    assert np.array_equal(host(f.neighborhood), w["neighborhood"])
+    mask = host(f.mask).astype(bool)
+    assert (mask.sum(1) == M).all()
+    gt = w["neighborhood"][mask]
+    d1, d2, i1, i2 = co.chamfer_fwd(pred, gt)
+    assert np.array_equal(host(f.dist1), d1) and np.array_equal(host(f.dist2), d2)
+    assert np.array_equal(host(f.idx1), i1) and np.array_equal(host(f.idx2), i2)
+    pp = co.chamfer_per_patch(d1, d2, norm)
+    assert np.allclose(host(f.per_patch), pp, rtol=RTOL, atol=0)
+    assert abs(f.total.item() - pp.mean()) <= RTOL * abs(pp.mean())
+    if norm == 2:
+        g = np.full((B * M, k), 1.0 / (B * M * k), dtype=np.float32)
+        ga, _ = co.chamfer_bwd(pred, gt, i1, i2, g, g)
+        assert np.abs(host(f.grad_pred) - ga).max() <= RTOL * np.abs(ga).max()
+    # second run through a captured graph gives the same bits (ticket self-reset, no stale state)
+    before = {n: host(getattr(f, n)).copy() for n in ("neighborhood", "grad_pred", "total", "mask")}
+    f.capture()
+    f.run(); f.run()
+    torch.cuda.synchronize()
+    for n, v in before.items():
+        assert np.array_equal(host(getattr(f, n)), v), n
+
+
+def test_cloud_step_rejects_unsupported(cuda):
+    from gm3d_b200 import _lib
+    from gm3d_b200.pipeline import GroupLossStep
+    with pytest.raises(NotImplementedError):
+        GroupLossStep(2, 4096, 64, 32, device=cuda, fused=True)
+    s = GroupLossStep(2, 4096, 64, 32, device=cuda)  # falls back to the kernel sequence by itself
+    assert not s.fused
+    lib = _lib.load()
+    p = s.xyz.data_ptr()
+    assert lib.gm3d_cloud_step_f32(p, 2, 4096, 64, 32, p, p, None, p, None, None, 0, 0, None, 0, 0, None, None, None,
+                                   0.0, 0.0, 2, None, None, None, None, None, None, None, None, None, None) == _lib.GM3D_ENOSUP
