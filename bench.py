@@ -157,7 +157,7 @@ def run_native(args, cfg):
     import torch.distributed as dist
 
     from gm3d_b200 import _lib
-    from gm3d_b200.pipeline import KERNELS_PER_STEP, GroupLossStep, HostStagedStep
+    from gm3d_b200.pipeline import GroupLossStep, HostStagedStep, StepRing
 
     _lib.load()  # fail loudly if the CUDA library is missing
     if not torch.cuda.is_available():
@@ -204,19 +204,32 @@ def run_native(args, cfg):
         for s in steps:
             s.graph = None
             s.capture(None)
+    # The steps of the ring share no buffer: at N = 1 (no collective between them) the whole ring is also
+    # captured as ONE graph whose fused kernels are chained by programmatic dependent launch.
+    ring_graph = None
+    if world == 1 and not args.no_overlap and steps[0].fused and ring > 1:
+        ring_graph = StepRing(steps).capture()
 
     def run_steps(n, start=0):
-        for i in range(n):
-            s = steps[(start + i) % ring]
+        i = 0
+        while i < n:
+            pos = (start + i) % ring
+            if ring_graph is not None and pos == 0 and n - i >= ring:
+                ring_graph.run()
+                i += ring
+                continue
+            s = steps[pos]
             s.run()
             if world > 1 and not collective_in_graph:
                 dist.all_reduce(s.stats[:3])
+            i += 1
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    W = -(-W // ring) * ring if ring_graph is not None else W  # warm-up ends on a ring boundary
     run_steps(W)
     barrier()
     clocks = ClockSampler(local)
@@ -373,8 +386,10 @@ def run_native(args, cfg):
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc, "B_per_gpu": B, "N": N, "G": G, "k": k, "M": M,
                            "l2_policy": f"inputs larger than L2: ring of {ring} buffer sets x {per_set / 1e6:.1f} MB",
-                           "cuda_graph": True, "collective": ("in-graph" if collective_in_graph else "eager") if world > 1 else "none"},
-                "clocks": clk, "e2e": e2e, "gpu_launches": KERNELS_PER_STEP * K,
+                           "cuda_graph": True,
+                           "step_overlap": (f"programmatic dependent launch inside one graph of {ring} steps" if ring_graph is not None else "none"),
+                           "kernels_per_step": steps[0].kernels_per_step, "collective": ("in-graph" if collective_in_graph else "eager") if world > 1 else "none"},
+                "clocks": clk, "e2e": e2e, "gpu_launches": steps[0].kernels_per_step * K,
                 "roofline": roofline, "roofline_detail": detail,
                 "step_hbm": {"algorithmic_bytes_per_step": step_bytes,
                              "gbs": step_bytes / (ms / K * 1e-3) / 1e9, "frac": step_bytes / (ms / K * 1e-3) / 1e9 / hbm_peak},
@@ -399,6 +414,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="one graph per step, no programmatic dependent launch")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":

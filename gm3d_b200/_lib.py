@@ -16,6 +16,7 @@ GM3D_EINVAL, GM3D_ENOSUP, GM3D_EALIGN = -1, -2, -3
 OP_FPS, OP_KNN, OP_GROUP, OP_CHAMFER_FWD, OP_CHAMFER_BWD, OP_HARD_MASK, OP_LOSS_STATS, OP_CLOUD_STEP = range(1, 9)
 KNN_MAX_K = 32
 LOSS_STATS_LEN = 8
+STEP_OVERLAP_NEXT, STEP_OVERLAP_PREV = 1, 2
 
 _vp, _i, _u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
 
@@ -37,7 +38,7 @@ SIGNATURES = {
     "gm3d_hard_mask_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _u64, _u64, _vp, _vp, _vp]),
     "gm3d_loss_stats_f32": (_i, [_vp, _i, _vp, _vp]),
     "gm3d_cloud_step_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _u64, _u64, _vp, _vp, _vp,
-                                 ctypes.c_float, ctypes.c_float, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                 ctypes.c_float, ctypes.c_float, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
 }
 
 _lib = None

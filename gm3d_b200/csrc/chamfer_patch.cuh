@@ -21,7 +21,8 @@ namespace gm3d {
 struct ChamferWarpScratch {  // per warp, 16-byte aligned
     float4 bxy[16];          // {x_2p, x_2p+1, y_2p, y_2p+1}
     float2 bz[16];           // {z_2p, z_2p+1}
-    float g2[32];            // 2 * upstream gradient of dist2[j]
+    float4 bg[32];           // {x_j, y_j, z_j, 2 * upstream gradient of dist2[j]}: one LDS.128 per scatter source
+    uint2 col[32];           // direction 2: {minimum bits, ballot of the lanes holding it} of column j
     unsigned in[32];         // incoming-source masks of the backward
 };
 
@@ -38,14 +39,16 @@ __device__ __forceinline__ ChamferWarpOut chamfer_patch_warp(float ax, float ay,
                                                              ChamferWarpScratch* __restrict__ sc) {
     const float inf = __int_as_float(0x7f800000);
     const bool live = lane < k;
-    // stage b (padding lanes: +inf coordinates => +inf distance, never a minimum)
+    // Padding lanes (k < 32): +inf coordinates on both sides, so a padded target is never a row minimum and a
+    // padded prediction row is all +inf / NaN (NaN bit patterns order above +inf) and never a column minimum.
+    if (!live) ax = ay = az = bx = by = bz = inf;
     {
         float* xy = reinterpret_cast<float*>(sc->bxy);
         float* zz = reinterpret_cast<float*>(sc->bz);
         const int p = lane >> 1, e = lane & 1;
-        xy[p * 4 + e] = live ? bx : inf;
-        xy[p * 4 + 2 + e] = live ? by : inf;
-        zz[p * 2 + e] = live ? bz : inf;
+        xy[p * 4 + e] = bx;
+        xy[p * 4 + 2 + e] = by;
+        zz[p * 2 + e] = bz;
     }
     __syncwarp();
     const float2 ax2 = make_float2(ax, ax), ay2 = make_float2(ay, ay), az2 = make_float2(az, az);
@@ -62,19 +65,19 @@ __device__ __forceinline__ ChamferWarpOut chamfer_patch_warp(float ax, float ay,
         if (d.x < best1) best1 = d.x, besti1 = 2 * p;
         if (d.y < best1) best1 = d.y, besti1 = 2 * p + 1;
     }
-    // direction 2: column minima over the live lanes
-    float best2 = inf;
-    int besti2 = 0;
+    // direction 2: column minima over the lanes.  The REDUX result and the ballot are warp-uniform; one lane
+    // parks them in shared memory and lane j picks column j up afterwards (no per-column selects).
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        const unsigned bits = live ? __float_as_uint(D[j]) : 0xffffffffu;
+        const unsigned bits = __float_as_uint(D[j]);
         const unsigned mn = __reduce_min_sync(kFull, bits);
         const unsigned bal = __ballot_sync(kFull, bits == mn);
-        if (lane == j) {
-            best2 = __uint_as_float(mn);
-            besti2 = __ffs(bal) - 1;
-        }
+        if (lane == 0) sc->col[j] = make_uint2(mn, bal);
     }
+    __syncwarp();
+    const uint2 cj = sc->col[lane];
+    const float best2 = __uint_as_float(cj.x);
+    const int besti2 = __ffs(cj.y) - 1;  // lowest lane = upstream's first minimum
     ChamferWarpOut o;
     o.dist1 = best1, o.dist2 = best2, o.idx1 = besti1, o.idx2 = besti2;
     const float f1 = live ? (norm == 1 ? __fsqrt_rn(best1) : best1) : 0.0f;
@@ -92,7 +95,7 @@ __device__ __forceinline__ ChamferWarpOut chamfer_patch_warp(float ax, float ay,
     const float u1 = norm == 1 ? __fmul_rn(gscale1, __fdiv_rn(0.5f, f1)) : gscale1;
     const float u2 = norm == 1 ? __fmul_rn(gscale2, __fdiv_rn(0.5f, f2)) : gscale2;
     const float g1 = __fmul_rn(u1, 2.0f), g2 = __fmul_rn(u2, 2.0f);
-    sc->g2[lane] = g2;
+    sc->bg[lane] = make_float4(bx, by, bz, g2);
     sc->in[lane] = 0u;
     __syncwarp();
     // lanes j whose arg-min is point i form a MATCH.ANY group; every member drops the group mask at in[i]
@@ -100,22 +103,18 @@ __device__ __forceinline__ ChamferWarpOut chamfer_patch_warp(float ax, float ay,
     if (live) sc->in[besti2] = peers;
     __syncwarp();
     unsigned sources = sc->in[lane];
-    const float* xy = reinterpret_cast<const float*>(sc->bxy);
-    const float* zz = reinterpret_cast<const float*>(sc->bz);
     float gx, gy, gz;
     {
-        const int j = besti1;
-        const float qx = xy[(j >> 1) * 4 + (j & 1)], qy = xy[(j >> 1) * 4 + 2 + (j & 1)], qz = zz[j];
-        gx = __fmul_rn(g1, ax - qx), gy = __fmul_rn(g1, ay - qy), gz = __fmul_rn(g1, az - qz);
+        const float4 q = sc->bg[besti1];
+        gx = __fmul_rn(g1, ax - q.x), gy = __fmul_rn(g1, ay - q.y), gz = __fmul_rn(g1, az - q.z);
     }
     while (sources) {  // ascending j: fixed summation order (= the oracle's)
         const int j = __ffs(sources) - 1;
         sources &= sources - 1;
-        const float h = sc->g2[j];
-        const float qx = xy[(j >> 1) * 4 + (j & 1)], qy = xy[(j >> 1) * 4 + 2 + (j & 1)], qz = zz[j];
-        gx = __fsub_rn(gx, __fmul_rn(h, qx - ax));
-        gy = __fsub_rn(gy, __fmul_rn(h, qy - ay));
-        gz = __fsub_rn(gz, __fmul_rn(h, qz - az));
+        const float4 q = sc->bg[j];
+        gx = __fsub_rn(gx, __fmul_rn(q.w, q.x - ax));
+        gy = __fsub_rn(gy, __fmul_rn(q.w, q.y - ay));
+        gz = __fsub_rn(gz, __fmul_rn(q.w, q.z - az));
     }
     o.gx = gx, o.gy = gy, o.gz = gz;
     __syncwarp();

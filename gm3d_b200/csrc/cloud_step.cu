@@ -23,6 +23,7 @@
 // /root/reference/Point-MAE_SA3D/engine_pretrain_Classifier_SVM.py:108-118,157-184;
 // models_mae_learn_loss_Classifier_SVM_feature_besed.py:1238-1260,1062-1109; ..._Classifier_SVM.py:968-982.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "chamfer_patch.cuh"
 #include "knn_select.cuh"
@@ -57,12 +58,14 @@ struct CloudStepParams {
     float *per_patch, *total, *stats, *gxyz1;
     unsigned* ticket;
     int use_bulk;
+    int flags;     // GM3D_STEP_* bits
+    int dbg_mode;  // tuning aid (GM3D_CS_MODE): 1 = sampler only, 2 = no loss work, 3 = prologue/epilogue only
     int npad;  // SoA length per coordinate: max(1024, N rounded up to 128)
     int LP;    // G rounded up to a power of two (>= 64)
 };
 
 struct CloudStepSmem {  // offsets into dynamic shared memory
-    size_t sx, sy, sz, aos, sel, cand, patch, cham, key, msel, mrank, total;
+    size_t sx, sy, sz, aos, sel, cand, cham, key, msel, mrank, total;
 };
 
 __host__ __device__ inline CloudStepSmem cloud_step_layout(int N, int G, int npad, int LP, int warps, bool loss) {
@@ -79,7 +82,6 @@ __host__ __device__ inline CloudStepSmem cloud_step_layout(int N, int G, int npa
     L.aos = take(static_cast<size_t>((N + 3) & ~3) * 12);
     L.sel = take(static_cast<size_t>(G) * 4);
     L.cand = take(static_cast<size_t>(warps) * 64 * 8);
-    L.patch = take(static_cast<size_t>(warps) * 96 * 4);
     L.cham = loss ? take(static_cast<size_t>(warps) * sizeof(ChamferWarpScratch)) : 0;
     L.key = (loss && LP > 64) ? take(static_cast<size_t>(LP) * 8) : 0;
     L.msel = loss ? take(static_cast<size_t>(LP)) : 0;
@@ -98,14 +100,25 @@ __device__ __forceinline__ void st_volatile_s32(int* p, int v) {
     asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 
+static __device__ __noinline__ void final_loss_reduce_cold(const float* per_patch, int P, float* total, float* stats) {
+    final_loss_reduce(per_patch, P, total, stats);
+}
+static __device__ __noinline__ void hard_mask_row_cold(const float* lrow, int L, int LP, int len_keep, int len_loss,
+                                                const float* rrow, uint64_t seed, uint64_t ctr, int row_id, uint8_t* mrow,
+                                                int32_t* prow, unsigned long long* s_key, uint8_t* s_sel, int lane) {
+    hard_mask_row(lrow, L, LP, len_keep, len_loss, rrow, seed, ctr, row_id, mrow, prow, s_key, s_sel, lane, 32, SyncWarp());
+}
+
 template <int PPT, int WARPS, bool LOSS>
 __global__ void __launch_bounds__(WARPS * 32, 1) cloud_step_kernel(const __grid_constant__ CloudStepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int2 s_red[2][kCsFpsWarps];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ int s_next;        // next patch id to hand out
     __shared__ int s_mask_ready;  // 1 once s_msel / s_mrank are valid
 
+    // Programmatic dependent launch: the caller promised that the next kernel in the stream touches none of
+    // this launch's buffers, so it may start filling SMs as soon as every CTA of this grid is resident.
+    if (p.flags & GM3D_STEP_OVERLAP_NEXT) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int N = p.N, G = p.G, k = p.k;
     const CloudStepSmem L = cloud_step_layout(N, G, p.npad, p.LP, WARPS, LOSS);
     float* sx = reinterpret_cast<float*>(smem_raw + L.sx);
@@ -128,7 +141,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cloud_step_kernel(const __grid_
         }
     }
     for (int g = tid; g < G; g += WARPS * 32) s_sel[g] = g == 0 ? 0 : -1;  // FPS starts at point 0
-    if (tid == 0) s_next = 0, s_mask_ready = 0;
+    if (tid == 0) s_mask_ready = 0;
     __syncthreads();
     if (p.use_bulk) {
         if (tid == 0) {
@@ -138,6 +151,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cloud_step_kernel(const __grid_
         }
     }
 
+    // 32-warp variant: the launch gives every thread 64 registers; the two sampler warpgroups release down to
+    // 40 and the six worker warpgroups take 72 (8*32*40 + 24*32*72 = 65536 = the whole register file).
+    if (WARPS == 32) {
+        if (warp < kCsFpsWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");
+    }
     float2 X[PPT / 2], Y[PPT / 2], Z[PPT / 2], T[PPT / 2];
     if (warp < kCsFpsWarps) {
         if (p.use_bulk) mbar_wait(&s_bar, 0);
@@ -163,7 +182,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cloud_step_kernel(const __grid_
     if (warp < kCsFpsWarps) {
         // ---------------- sampler: G - 1 dependent rounds
         int old = 0;
-        for (int j = 1; j < G; ++j) {
+        for (int j = 1; j < (p.dbg_mode == 3 ? 1 : G); ++j) {
             const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
             const float2 x2 = make_float2(x1, x1), y2 = make_float2(y1, y1), z2 = make_float2(z1, z1);
             float m[PPT];
@@ -215,8 +234,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cloud_step_kernel(const __grid_
         if (p.LP <= 64) {
             hard_mask_row_warp64(lrow, G, p.len_keep, p.len_loss, rrow, p.seed, ctr, b, mrow, prow, s_msel, lane);
         } else {
-            hard_mask_row(lrow, G, p.LP, p.len_keep, p.len_loss, rrow, p.seed, ctr, b, mrow, prow,
-                          reinterpret_cast<unsigned long long*>(smem_raw + L.key), s_msel, lane, 32, SyncWarp());
+            hard_mask_row_cold(lrow, G, p.LP, p.len_keep, p.len_loss, rrow, p.seed, ctr, b, mrow, prow,
+                               reinterpret_cast<unsigned long long*>(smem_raw + L.key), s_msel, lane);
         }
         __syncwarp();
         int base = 0;
@@ -232,76 +251,62 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cloud_step_kernel(const __grid_
         if (lane == 0) st_volatile_s32(&s_mask_ready, 1);
     }
 
-    // ---------------- workers: one patch per trip
-    u64* cb = reinterpret_cast<u64*>(smem_raw + L.cand) + warp * 64;
-    float* s_patch = reinterpret_cast<float*>(smem_raw + L.patch) + warp * 96;
-    ChamferWarpScratch* csc = LOSS ? reinterpret_cast<ChamferWarpScratch*>(smem_raw + L.cham) + warp : nullptr;
-    for (;;) {
-        int g = 0;
-        if (lane == 0) g = atomicAdd(&s_next, 1);
-        g = __shfl_sync(kFull, g, 0);
-        if (g >= G) break;
-        int c;
-        while ((c = ld_volatile_s32(&s_sel[g])) < 0) __nanosleep(40);
-        const float qx = sx[c], qy = sy[c], qz = sz[c];
-
-        KnnStream<1> st;
-        st.qx[0] = qx, st.qy[0] = qy, st.qz[0] = qz;
-        st.cnt[0] = 0;
-        if (!bootstrap_query(sx, sy, sz, 0, qx, qy, qz, k, lane, cb, st.top[0], st.thr[0])) {
-            st.thr[0] = __uint_as_float(kFltMaxBits);
-            st.top[0] = kKeyInf;
-            stream_tile<1>(st, sx, sy, sz, 0, min(N, kKnnTile), k, lane, cb);
-        }
-        if (N > kKnnTile) stream_tile<1>(st, sx + kKnnTile, sy + kKnnTile, sz + kKnnTile, kKnnTile, N - kKnnTile, k, lane, cb);
-        knn_finish<1>(st, 0, cb, lane);
-
-        // gather + centre-normalise; lane l < k owns neighbour l
-        const unsigned pi = lane < k ? static_cast<unsigned>(st.top[0] & 0xffffffffu) : 0u;
-        const float ox = sx[pi], oy = sy[pi], oz = sz[pi];
-        const float bx = __fsub_rn(ox, qx), by = __fsub_rn(oy, qy), bz = __fsub_rn(oz, qz);
-        const size_t row = (static_cast<size_t>(b) * G + g) * k;
-        if (p.knn_idx && lane < k) p.knn_idx[row + lane] = static_cast<int64_t>(pi);
+    // ---------------- workers: patch g = worker, worker + #workers, ... (centres appear in that order)
+    if (warp >= kCsFpsWarps) {
+        u64* cb = reinterpret_cast<u64*>(smem_raw + L.cand) + warp * 64;
+        ChamferWarpScratch* csc = LOSS ? reinterpret_cast<ChamferWarpScratch*>(smem_raw + L.cham) + warp : nullptr;
         const int nf = 3 * k;  // floats per patch
-        if (p.nbhd_org) {
-            __syncwarp();
-            if (lane < k) s_patch[3 * lane] = ox, s_patch[3 * lane + 1] = oy, s_patch[3 * lane + 2] = oz;
-            __syncwarp();
-            for (int t = lane; t < nf; t += 32) p.nbhd_org[row * 3 + t] = s_patch[t];
-        }
-        __syncwarp();
-        if (lane < k) s_patch[3 * lane] = bx, s_patch[3 * lane + 1] = by, s_patch[3 * lane + 2] = bz;
-        __syncwarp();
-        for (int t = lane; t < nf; t += 32) p.nbhd[row * 3 + t] = s_patch[t];
+        for (int g = warp - kCsFpsWarps; g < G; g += WARPS - kCsFpsWarps) {
+            if (p.dbg_mode == 1 || p.dbg_mode == 3) break;
+            int c;
+            while ((c = ld_volatile_s32(&s_sel[g])) < 0) __nanosleep(64);
+            const float qx = sx[c], qy = sy[c], qz = sz[c];
+            u64 top;
+            float thr;
+            if (!bootstrap_query(sx, sy, sz, 0, qx, qy, qz, k, lane, cb, top, thr))  // tiny cloud / heavy ties
+                top = knn_stream_points(kKeyInf, __uint_as_float(kFltMaxBits), sx, sy, sz, 0, N, qx, qy, qz, k, lane, cb);
+            else if (N > kKnnTile)
+                top = knn_stream_points(top, thr, sx + kKnnTile, sy + kKnnTile, sz + kKnnTile, kKnnTile, N - kKnnTile, qx,
+                                        qy, qz, k, lane, cb);
 
-        if (LOSS) {
-            while (ld_volatile_s32(&s_mask_ready) == 0) __nanosleep(40);
-            const int mr = s_mrank[g];
-            if (mr >= 0) {  // warp-uniform
-                const size_t pp = static_cast<size_t>(b) * M + mr;
-                const float* pa = p.pred + pp * nf;
-                __syncwarp();
-                for (int t = lane; t < nf; t += 32) s_patch[t] = __ldg(pa + t);
-                __syncwarp();
-                const int ls = lane < k ? lane : 0;
-                const float ax = s_patch[3 * ls], ay = s_patch[3 * ls + 1], az = s_patch[3 * ls + 2];
-                const ChamferWarpOut o = chamfer_patch_warp(ax, ay, az, bx, by, bz, k, p.norm, p.gscale1, p.gscale2, lane, csc);
-                if (lane < k) {
-                    if (p.dist1) p.dist1[pp * k + lane] = o.dist1;
-                    if (p.dist2) p.dist2[pp * k + lane] = o.dist2;
-                    if (p.idx1) p.idx1[pp * k + lane] = o.idx1;
-                    if (p.idx2) p.idx2[pp * k + lane] = o.idx2;
-                    s_patch[3 * lane] = o.gx, s_patch[3 * lane + 1] = o.gy, s_patch[3 * lane + 2] = o.gz;
+            // gather + centre-normalise; lane l < k owns neighbour l
+            const unsigned pi = lane < k ? static_cast<unsigned>(top & 0xffffffffu) : 0u;
+            const float ox = sx[pi], oy = sy[pi], oz = sz[pi];
+            const float bx = __fsub_rn(ox, qx), by = __fsub_rn(oy, qy), bz = __fsub_rn(oz, qz);
+            const size_t row = (static_cast<size_t>(b) * G + g) * k;
+            if (lane < k) {
+                if (p.knn_idx) p.knn_idx[row + lane] = static_cast<int64_t>(pi);
+                if (p.nbhd_org) {
+                    float* o = p.nbhd_org + (row + lane) * 3;
+                    o[0] = ox, o[1] = oy, o[2] = oz;
                 }
-                if (lane == 0 && p.per_patch) p.per_patch[pp] = o.per_patch;
-                __syncwarp();
-                for (int t = lane; t < nf; t += 32) p.gxyz1[pp * nf + t] = s_patch[t];
+                float* o = p.nbhd + (row + lane) * 3;
+                o[0] = bx, o[1] = by, o[2] = bz;
+            }
+            if (LOSS && p.dbg_mode != 2) {
+                while (ld_volatile_s32(&s_mask_ready) == 0) __nanosleep(64);
+                const int mr = s_mrank[g];
+                if (mr >= 0) {  // warp-uniform: patch g is masked, its prediction is row b*M + mr
+                    const size_t pp = static_cast<size_t>(b) * M + mr;
+                    const float* pa = p.pred + pp * nf + 3 * (lane < k ? lane : 0);
+                    const float ax = __ldg(pa), ay = __ldg(pa + 1), az = __ldg(pa + 2);
+                    const ChamferWarpOut o = chamfer_patch_warp(ax, ay, az, bx, by, bz, k, p.norm, p.gscale1, p.gscale2, lane, csc);
+                    if (lane < k) {
+                        if (p.dist1) p.dist1[pp * k + lane] = o.dist1;
+                        if (p.dist2) p.dist2[pp * k + lane] = o.dist2;
+                        if (p.idx1) p.idx1[pp * k + lane] = o.idx1;
+                        if (p.idx2) p.idx2[pp * k + lane] = o.idx2;
+                        float* go = p.gxyz1 + pp * nf + 3 * lane;
+                        go[0] = o.gx, go[1] = o.gy, go[2] = o.gz;
+                    }
+                    if (lane == 0 && p.per_patch) p.per_patch[pp] = o.per_patch;
+                }
             }
         }
     }
 
     if (LOSS && p.ticket) {
-        if (last_cta(p.ticket)) final_loss_reduce(p.per_patch, p.B * M, p.total, p.stats);
+        if (last_cta(p.ticket)) final_loss_reduce_cold(p.per_patch, p.B * M, p.total, p.stats);
     }
 }
 
@@ -314,8 +319,15 @@ static int launch_cloud_step(const CloudStepParams& p, size_t smem, cudaStream_t
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return static_cast<int>(e);
     }
-    kern<<<p.B, WARPS * 32, smem, st>>>(p);
-    return launch_status();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.B), cfg.blockDim = dim3(WARPS * 32), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (p.flags & GM3D_STEP_OVERLAP_PREV) ? 1 : 0;  // this launch need not wait for its predecessor
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+    return e == cudaSuccess ? launch_status() : static_cast<int>(e);
 }
 
 constexpr int kCsWarps = 24;  // 8 sampler + 16 worker warps
@@ -325,6 +337,16 @@ constexpr int kCloudStepMaxN = kCsFpsThreads * 8;
 
 bool cloud_step_supported(int N, int G, int k) { return N <= kCloudStepMaxN && G <= 1024 && k <= 32 && N >= 1 && G <= N; }
 
+template <int WARPS>
+static int cloud_step_dispatch(CloudStepParams& p, bool loss, cudaStream_t st) {
+    const CloudStepSmem L = cloud_step_layout(p.N, p.G, p.npad, p.LP, WARPS, loss);
+    if (L.total > 200 * 1024) return GM3D_ENOSUP;
+    if (p.N <= kCsFpsThreads * 4) {
+        return loss ? launch_cloud_step<4, WARPS, true>(p, L.total, st) : launch_cloud_step<4, WARPS, false>(p, L.total, st);
+    }
+    return loss ? launch_cloud_step<8, WARPS, true>(p, L.total, st) : launch_cloud_step<8, WARPS, false>(p, L.total, st);
+}
+
 int cloud_step_launch(CloudStepParams p, cudaStream_t st) {
     const bool loss = p.pred != nullptr;
     p.npad = p.N <= kKnnTile ? kKnnTile : ((p.N + 127) & ~127);
@@ -332,12 +354,16 @@ int cloud_step_launch(CloudStepParams p, cudaStream_t st) {
     while (LP < p.G) LP <<= 1;
     p.LP = LP;
     p.use_bulk = (p.N % 4 == 0) && (reinterpret_cast<uintptr_t>(p.xyz) % 16 == 0);
-    const CloudStepSmem L = cloud_step_layout(p.N, p.G, p.npad, p.LP, kCsWarps, loss);
-    if (L.total > 200 * 1024) return GM3D_ENOSUP;
-    if (p.N <= kCsFpsThreads * 4) {
-        return loss ? launch_cloud_step<4, kCsWarps, true>(p, L.total, st) : launch_cloud_step<4, kCsWarps, false>(p, L.total, st);
+    static const int warps = getenv("GM3D_CS_WARPS") ? atoi(getenv("GM3D_CS_WARPS")) : kCsWarps;
+    static const int mode = getenv("GM3D_CS_MODE") ? atoi(getenv("GM3D_CS_MODE")) : 0;
+    p.dbg_mode = mode;
+    switch (warps) {
+        case 12: return cloud_step_dispatch<12>(p, loss, st);
+        case 16: return cloud_step_dispatch<16>(p, loss, st);
+        case 20: return cloud_step_dispatch<20>(p, loss, st);
+        case 32: return cloud_step_dispatch<32>(p, loss, st);
+        default: return cloud_step_dispatch<kCsWarps>(p, loss, st);
     }
-    return loss ? launch_cloud_step<8, kCsWarps, true>(p, L.total, st) : launch_cloud_step<8, kCsWarps, false>(p, L.total, st);
 }
 
 }  // namespace gm3d
@@ -347,13 +373,14 @@ GM3D_API int gm3d_cloud_step_f32(const float* xyz, int B, int N, int G, int k, i
                                  int len_loss, const float* rand_keys, uint64_t seed, uint64_t offset, uint8_t* mask,
                                  int32_t* patch_index, const float* pred, float gscale1, float gscale2, int norm,
                                  float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, float* per_patch, float* total,
-                                 float* stats, float* gxyz1, void* ws, void* stream) {
+                                 float* stats, float* gxyz1, int flags, void* ws, void* stream) {
     using namespace gm3d;
     if (!xyz || !fps_idx || !centers || !nbhd || B <= 0 || N <= 0 || G <= 0 || k <= 0 || k > N || G > N) return GM3D_EINVAL;
     if (!cloud_step_supported(N, G, k)) return GM3D_ENOSUP;
     CloudStepParams p{};
     p.xyz = xyz, p.B = B, p.N = N, p.G = G, p.k = k;
     p.fps_idx = fps_idx, p.centers = centers, p.knn_idx = knn_idx, p.nbhd = nbhd, p.nbhd_org = nbhd_org;
+    p.flags = flags;
     if (pred) {
         if (!mask || !gxyz1 || len_keep < 0 || len_keep >= G || len_loss < 0 || len_loss > G - len_keep) return GM3D_EINVAL;
         if (len_loss > 0 && !loss_pred) return GM3D_EINVAL;

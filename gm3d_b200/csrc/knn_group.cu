@@ -189,7 +189,7 @@ GM3D_API int gm3d_group_f32(const float* xyz, int B, int N, int G, int k, int32_
     if (N <= 2048 && G <= 1024)  // one CTA per cloud: sampling and patch selection overlapped (cloud_step.cu)
         return gm3d_cloud_step_f32(xyz, B, N, G, k, fps_idx, centers, knn_idx, nbhd, nbhd_org, nullptr, 0, 0, nullptr, 0, 0,
                                    nullptr, nullptr, nullptr, 0.f, 0.f, 2, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                   nullptr, nullptr, nullptr, nullptr, stream);
+                                   nullptr, nullptr, nullptr, 0, nullptr, stream);
     int rc = gm3d_fps_f32(xyz, B, N, G, fps_idx, centers, ws, stream);
     if (rc != GM3D_OK) return rc;
     return launch_knn_group(xyz, centers, B, N, G, k, nullptr, knn_idx, nbhd, nbhd_org, as_stream(stream));

@@ -129,6 +129,13 @@ __device__ __forceinline__ u64 order_keys_exact(const u64* __restrict__ cb, int 
     return c;
 }
 
+// Cold path (ties): the 32 smallest of two keys per lane, ascending, by full 64-bit key sorts.
+static __device__ __noinline__ u64 order_two_exact(u64 c0, u64 c1, bool two, int lane) {
+    u64 top = bitonic_sort32(c0, lane);
+    if (two) top = merge_sorted32(top, bitonic_sort32(c1, lane), lane);
+    return top;
+}
+
 // Bootstrap one query on a full SoA tile.  On success `top` holds the tile's k nearest (ascending keys, lanes
 // >= k hold larger keys or the sentinel) and `thr` the k-th distance.  Returns false when more than 64
 // points pass the bound (heavy ties / tiny tiles): the caller then streams the tile instead.
@@ -216,8 +223,7 @@ __device__ __forceinline__ bool bootstrap_query(const float* __restrict__ sx, co
     const bool tie = (lane + 1 < k) && (srt == nxt);
     const int cnt = __popc(__ballot_sync(kFull, d0 <= thrb)) + __popc(__ballot_sync(kFull, d1 <= thrb));
     if (__any_sync(kFull, tie) || cnt != k) {  // bit-equal distances among the best k+1: exact 64-bit ordering
-        top = bitonic_sort32(c0, lane);
-        if (extra > 0) top = merge_sorted32(top, bitonic_sort32(c1, lane), lane);
+        top = order_two_exact(c0, c1, extra > 0, lane);
         thr = key_dist(__shfl_sync(kFull, top, k - 1));
         __syncwarp();
         return true;
@@ -317,6 +323,19 @@ __device__ __forceinline__ void knn_finish(KnnStream<Q>& s, int q, const u64* __
         s.top[q] = merge_sorted32(s.top[q], c, lane);
         s.cnt[q] = 0;
     }
+}
+
+// Out-of-line single-query helpers for callers that keep the hot path small (the fused per-cloud kernel).
+// knn_stream_points: continue a query whose k-list `top` / bound `thr` come from earlier tiles over the SoA
+// points [0, npts) at (sx, sy, sz) (global index base + i); returns the merged k-list.
+static __device__ __noinline__ u64 knn_stream_points(u64 top, float thr, const float* sx, const float* sy, const float* sz,
+                                              int base, int npts, float qx, float qy, float qz, int k, int lane, u64* cb) {
+    KnnStream<1> s;
+    s.qx[0] = qx, s.qy[0] = qy, s.qz[0] = qz, s.thr[0] = thr, s.top[0] = top, s.cnt[0] = 0;
+    for (int t0 = 0; t0 < npts; t0 += kKnnTile)
+        stream_tile<1>(s, sx + t0, sy + t0, sz + t0, base + t0, min(kKnnTile, npts - t0), k, lane, cb);
+    knn_finish<1>(s, 0, cb, lane);
+    return s.top[0];
 }
 
 // Cooperative AoS (xyz triples, shared or global) -> SoA conversion of `cnt` points by `nthreads` threads;

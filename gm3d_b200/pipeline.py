@@ -80,8 +80,9 @@ class GroupLossStep:
             "hard_mask": 5 * G + 4 * M,
         }
 
-    def enqueue(self) -> None:
-        """Enqueue the kernels of one step on torch's current stream (+ one forked side stream)."""
+    def enqueue(self, flags: int = 0) -> None:
+        """Enqueue the kernels of one step on torch's current stream (+ one forked side stream).  `flags`:
+        _lib.STEP_OVERLAP_* for the fused kernel (only between steps that share no buffer)."""
         L, p = self.lib, (lambda t: None if t is None else t.data_ptr())
         main = torch.cuda.current_stream(self.dev)
         st = main.cuda_stream
@@ -93,7 +94,7 @@ class GroupLossStep:
                 p(self.xyz), B, N, G, k, p(self.fps_idx), p(self.center), None, p(self.neighborhood), None,
                 p(self.loss_pred), self.len_keep, self.len_loss, None, self.seed, self.rand_offset, p(self.mask),
                 p(self.patch_index), p(self.pred), g, g, self.norm, p(self.dist1), p(self.dist2), p(self.idx1),
-                p(self.idx2), p(self.per_patch), p(self.total), p(self.stats), p(self.grad_pred), p(self.cd_ws), st))
+                p(self.idx2), p(self.per_patch), p(self.total), p(self.stats), p(self.grad_pred), flags, p(self.cd_ws), st))
             return
         # the mask depends only on loss_pred: fork it onto a side stream so that (also inside a captured
         # graph) it runs concurrently with FPS, which occupies one SM per cloud and leaves the rest idle
@@ -128,6 +129,45 @@ class GroupLossStep:
                 self.enqueue()
                 if extra is not None:
                     extra()
+            self.graph = g
+        return self
+
+    def run(self) -> None:
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.enqueue()
+
+
+class StepRing:
+    """A ring of GroupLossStep buffer sets replayed as ONE CUDA graph.  The steps share no buffer, so the fused
+    kernels are chained with programmatic dependent launch: step i+1 starts filling SMs while step i drains
+    (launch latency, the cold-cloud prologue and the last-CTA loss reduction of one step hide under the next)."""
+
+    def __init__(self, steps):
+        self.steps = list(steps)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+
+    def enqueue(self) -> None:
+        n = len(self.steps)
+        for i, s in enumerate(self.steps):
+            f = 0
+            if s.fused and n > 1:
+                f = (_lib.STEP_OVERLAP_NEXT if i + 1 < n else 0) | (_lib.STEP_OVERLAP_PREV if i > 0 else 0)
+            s.enqueue(f)
+
+    def capture(self) -> "StepRing":
+        dev = self.steps[0].dev
+        with torch.cuda.device(dev):
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self.enqueue()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.enqueue()
             self.graph = g
         return self
 

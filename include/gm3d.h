@@ -69,6 +69,13 @@ extern "C" {
 
 /* Largest k gm3d_knn_f32 / gm3d_group_f32 accept (one warp holds the sorted k-list, one entry per lane). */
 #define GM3D_KNN_MAX_K 32
+/* gm3d_cloud_step_f32 flags (programmatic dependent launch).  Stream order normally makes a kernel wait for
+ * the complete previous kernel; a step that shares NO buffer (inputs, outputs, workspace) with its stream
+ * neighbour may drop that wait so that consecutive steps overlap tail-to-head:
+ *   OVERLAP_NEXT  this launch lets the next kernel in the stream start while it is still running;
+ *   OVERLAP_PREV  this launch does not wait for the previous kernel (which must have OVERLAP_NEXT set). */
+#define GM3D_STEP_OVERLAP_NEXT 1
+#define GM3D_STEP_OVERLAP_PREV 2
 /* Number of floats gm3d_loss_stats_f32 writes. */
 #define GM3D_LOSS_STATS_LEN 8
 
@@ -184,7 +191,7 @@ int gm3d_cloud_step_f32(const float* xyz, int B, int N, int G, int k, int32_t* f
                         uint8_t* mask /* (B,G) */, int32_t* patch_index /* (B*M) or NULL */, const float* pred,
                         float gscale1, float gscale2, int norm /* 1|2 */, float* dist1, float* dist2, int32_t* idx1,
                         int32_t* idx2, float* per_patch, float* total, float* stats, float* gxyz1 /* (B*M,k,3) */,
-                        void* ws, void* stream);
+                        int flags /* GM3D_STEP_* or 0 */, void* ws, void* stream);
 
 #ifdef __cplusplus
 }

@@ -543,4 +543,31 @@ def test_cloud_step_rejects_unsupported(cuda):
     lib = _lib.load()
     p = s.xyz.data_ptr()
     assert lib.gm3d_cloud_step_f32(p, 2, 4096, 64, 32, p, p, None, p, None, None, 0, 0, None, 0, 0, None, None, None,
-                                   0.0, 0.0, 2, None, None, None, None, None, None, None, None, None, None) == _lib.GM3D_ENOSUP
+                                   0.0, 0.0, 2, None, None, None, None, None, None, None, None, 0, None, None) == _lib.GM3D_ENOSUP
+
+
+def test_step_ring_overlapped_steps_equal_serial_steps(cuda):
+    """A ring of buffer sets replayed as one graph with programmatic dependent launch between the fused kernels
+    (steps overlap tail-to-head) gives, for every step, the bits of the same step run alone."""
+    from gm3d_b200.pipeline import GroupLossStep, StepRing
+    B, N, G, k = 16, 1024, 64, 32
+    rng = np.random.default_rng(9)
+    steps, want = [], []
+    for r in range(6):
+        s = GroupLossStep(B, N, G, k, 0.6, device=cuda, seed=4, rand_offset=r * B * G)
+        s.xyz.copy_(dev(synthetic_clouds(B, N, 300 + r), cuda))
+        s.loss_pred.copy_(dev(rng.standard_normal((B, G)).astype(np.float32), cuda))
+        s.pred.copy_(dev((rng.standard_normal((s.P, k, 3)) * 0.08).astype(np.float32), cuda))
+        s.run()
+        torch.cuda.synchronize()
+        want.append({n: host(getattr(s, n)).copy() for n in ("fps_idx", "neighborhood", "mask", "per_patch", "total", "stats", "grad_pred")})
+        for n in want[-1]:
+            getattr(s, n).fill_(0)
+        steps.append(s)
+    ring = StepRing(steps).capture()
+    for _ in range(3):
+        ring.run()
+    torch.cuda.synchronize()
+    for s, w in zip(steps, want):
+        for n, v in w.items():
+            assert np.array_equal(host(getattr(s, n)), v), n

@@ -20,7 +20,7 @@ ap.add_argument("--only", default="")
 a = ap.parse_args()
 B, N, G, k, ratio, _ = CONFIGS[a.config]
 dev = torch.device("cuda", 0)
-s = GroupLossStep(B, N, G, k, ratio, device=dev, seed=1)
+s = GroupLossStep(B, N, G, k, ratio, device=dev, seed=1, fused=False)
 x, lp, pred = synthetic_batch(B, N, G, k, s.M, 1234)
 s.xyz.copy_(torch.from_numpy(x)); s.loss_pred.copy_(torch.from_numpy(lp)); s.pred.copy_(torch.from_numpy(pred))
 L = _lib.load()
@@ -37,6 +37,11 @@ kern = {
                                                       p(s.dist2), p(s.idx1), p(s.idx2), p(s.per_patch), p(s.total), p(s.stats), 2,
                                                       p(s.grad_pred), None, p(s.cd_ws), st),
 }
+if N <= 2048:
+    kern["cloud_step"] = lambda: L.gm3d_cloud_step_f32(
+        p(s.xyz), B, N, G, k, p(s.fps_idx), p(s.center), None, p(s.neighborhood), None, p(s.loss_pred), s.len_keep,
+        s.len_loss, None, 1, 0, p(s.mask), p(s.patch_index), p(s.pred), g, g, 2, p(s.dist1), p(s.dist2), p(s.idx1),
+        p(s.idx2), p(s.per_patch), p(s.total), p(s.stats), p(s.grad_pred), 0, p(s.cd_ws), st)
 for name, fn in kern.items():
     if a.only and a.only != name:
         continue
