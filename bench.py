@@ -152,6 +152,12 @@ def run_reference(args, cfg):
 
 
 # ------------------------------------------------------------------------------------------ native arm
+def _stage(msg):
+    if os.environ.get("GM3D_BENCH_TRACE"):
+        sys.stderr.write(f"[bench r{os.environ.get('RANK', '0')} {time.time() % 1000:8.3f}] {msg}\n")
+        sys.stderr.flush()
+
+
 def run_native(args, cfg):
     import torch
     import torch.distributed as dist
@@ -175,15 +181,11 @@ def run_native(args, cfg):
 
     # ring of buffer sets larger than L2 so every step reads cold inputs and writes cold outputs
     probe = GroupLossStep(B, N, G, k, ratio, device=dev)
-    per_set = sum(t.numel() * t.element_size() for t in vars(probe).values() if isinstance(t, torch.Tensor))
+    per_set = sum({t.untyped_storage().data_ptr(): t.untyped_storage().nbytes()
+                   for t in vars(probe).values() if isinstance(t, torch.Tensor)}.values())  # views share storage
     ring = int(min(64, max(4, -(-2 * L2_BYTES // per_set))))
     M = probe.M
     del probe
-
-    def allreduce_stats(step):
-        if world > 1:
-            return lambda: dist.all_reduce(step.stats[:3])
-        return None
 
     steps = []
     for r in range(ring):
@@ -191,55 +193,64 @@ def run_native(args, cfg):
         x, lp, pred = synthetic_batch(B, N, G, k, M, 1234 + 1000 * rank + r)
         s.xyz.copy_(torch.from_numpy(x)); s.loss_pred.copy_(torch.from_numpy(lp)); s.pred.copy_(torch.from_numpy(pred))
         steps.append(s)
-    collective_in_graph = world > 1
-    try:
-        for s in steps:
-            s.capture(allreduce_stats(s))
-    except Exception as e:  # NCCL not capturable here: keep the graph for the kernels, all-reduce eagerly
-        if world == 1:
-            raise
-        collective_in_graph = False
-        sys.stderr.write(f"[bench] all-reduce not captured ({e}); issuing it eagerly after each graph\n")
-        torch.cuda.synchronize()
-        for s in steps:
-            s.graph = None
-            s.capture(None)
-    # The steps of the ring share no buffer: at N = 1 (no collective between them) the whole ring is also
-    # captured as ONE graph whose fused kernels are chained by programmatic dependent launch.
-    ring_graph = None
-    if world == 1 and not args.no_overlap and steps[0].fused and ring > 1:
-        ring_graph = StepRing(steps).capture()
 
-    def run_steps(n, start=0):
-        i = 0
-        while i < n:
-            pos = (start + i) % ring
-            if ring_graph is not None and pos == 0 and n - i >= ring:
-                ring_graph.run()
-                i += ring
-                continue
-            s = steps[pos]
-            s.run()
-            if world > 1 and not collective_in_graph:
-                dist.all_reduce(s.stats[:3])
-            i += 1
+    # K timed steps = q replays of the whole ring captured as ONE graph + one graph of the first K % ring steps.
+    # The steps of a ring share no buffer, so inside a graph the fused kernels are chained by programmatic
+    # dependent launch; with N > 1 each graph ends with ONE all-reduce of its steps' [sum, sum_sq, count].
+    # --no-overlap: one graph per step (kernel after kernel, one all-reduce per step).
+    overlap = not args.no_overlap
+    collective = "none"
+    chunks = {}
+
+    def chunk(n):
+        if n not in chunks:
+            if overlap:
+                chunks[n] = StepRing(steps[:n], reduce_stats=world > 1).capture()
+            else:
+                chunks[n] = [steps[i].capture((lambda s=steps[i]: dist.all_reduce(s.stats[:3])) if world > 1 else None)
+                             if steps[i].graph is None else steps[i] for i in range(n)]
+        return chunks[n]
+
+    if world > 1:
+        collective = "one NCCL all-reduce per graph of steps" if overlap else "one NCCL all-reduce per step, in-graph"
+
+    def run_chunk(n):
+        c = chunk(n)
+        if overlap:
+            c.run()
+        else:
+            for s in c:
+                s.run()
+
+    def run_steps(n):
+        for _ in range(n // ring):
+            run_chunk(ring)
+        if n % ring:
+            run_chunk(n % ring)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    W = -(-W // ring) * ring if ring_graph is not None else W  # warm-up ends on a ring boundary
-    run_steps(W)
+    _stage("buffers ready; capturing")
+    chunk(ring)
+    _stage("ring captured")
+    if K % ring:
+        chunk(K % ring)
+    _stage("warm-up")
+    run_steps(max(W, ring))  # at least one pass over every buffer set
+    run_steps(K)             # and one pass over exactly the graphs that are timed
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
         time.sleep(0.15)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _stage("timed region")
     barrier()
     ev0.record()
-    run_steps(K, W)
+    run_steps(K)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -255,6 +266,7 @@ def run_native(args, cfg):
         ms = t.item()
     value = world * B * K / (ms * 1e-3)
 
+    _stage("timed region done")
     # ---- per-kernel device times (CUDA events on the launching stream, same ring => cold L2)
     per_kernel = {}
     if rank == 0:
@@ -275,6 +287,11 @@ def run_native(args, cfg):
             "hard_mask": lambda s, st: L.gm3d_hard_mask_f32(p(s.loss_pred), B, G, s.len_keep, s.len_loss, None, 1, 0,
                                                         p(s.mask), p(s.patch_index), st),
         }
+        if steps[0].fused:
+            launchers["cloud_step"] = lambda s, st: L.gm3d_cloud_step_f32(
+                p(s.xyz), B, N, G, k, p(s.fps_idx), p(s.center), None, p(s.neighborhood), None, p(s.loss_pred), s.len_keep,
+                s.len_loss, None, s.seed, s.rand_offset, p(s.mask), p(s.patch_index), p(s.pred), g, g, 2, p(s.dist1),
+                p(s.dist2), p(s.idx1), p(s.idx2), p(s.per_patch), p(s.total), p(s.stats), p(s.grad_pred), 0, p(s.cd_ws), st)
         for name, fn in launchers.items():
             # one graph holding `ring` launches of this kernel (one per buffer set => cold L2 every launch);
             # replayed so that host launch gaps do not pollute the per-launch time
@@ -302,26 +319,28 @@ def run_native(args, cfg):
             torch.cuda.synchronize()
             per_kernel[name] = a.elapsed_time(b) * 1e3 / (reps * ring)  # us per launch, back-to-back in a graph
 
+    _stage("e2e")
     # ---- end-to-end: every step fed from pinned host memory, results read back
-    e2e = None
-    hs = [HostStagedStep(B, N, G, k, ratio, device=dev, seed=1234, rand_offset=r * B * G) for r in range(2)]
+    NSLOT = 4
+    hs = [HostStagedStep(B, N, G, k, ratio, device=dev, seed=1234, rand_offset=r * B * G) for r in range(NSLOT)]
     for r, s in enumerate(hs):
         x, lp, pred = synthetic_batch(B, N, G, k, M, 4321 + 1000 * rank + r)
         s.h_xyz.copy_(torch.from_numpy(x)); s.h_pred.copy_(torch.from_numpy(pred)); s.h_loss_pred.copy_(torch.from_numpy(lp))
-    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    streams = [torch.cuda.Stream(dev) for _ in range(NSLOT)]
     for s, strm in zip(hs, streams):
         with torch.cuda.stream(strm):
             s.capture(None)
     torch.cuda.synchronize()
-    Ke = K
+    Ke = max(K, 240)  # the host-fed pipeline needs a few hundred steps to reach steady state
     losses = []
 
     def e2e_steps(n):
-        # two slots on two streams: copies of one step overlap the kernels of the other; the host reads each
-        # slot's loss (pinned h_stats) before re-using the slot
-        pending = [None, None]
+        # NSLOT slots on NSLOT streams, each slot's graph = [one H2D copy, the step, one D2H copy]: the copies of
+        # one step overlap the kernels of the others; the host reads a slot's loss (pinned h_stats) before it
+        # re-uses the slot, i.e. every step's result reaches the host inside the timed region
+        pending = [None] * NSLOT
         for i in range(n):
-            j = i & 1
+            j = i % NSLOT
             if pending[j] is not None:
                 pending[j].synchronize()
                 losses.append(float(hs[j].h_stats[0]))
@@ -329,13 +348,12 @@ def run_native(args, cfg):
                 hs[j].run()
                 ev = torch.cuda.Event()
                 ev.record()
-            if world > 1:
-                pass  # statistics all-reduce is part of the device-timed arm; e2e measures the host-fed path per rank
             pending[j] = ev
-        for j in range(2):
-            if pending[j] is not None:
-                pending[j].synchronize()
-                losses.append(float(hs[j].h_stats[0]))
+        for j in range(NSLOT):
+            jj = (n + j) % NSLOT
+            if pending[jj] is not None:
+                pending[jj].synchronize()
+                losses.append(float(hs[jj].h_stats[0]))
 
     e2e_steps(W)
     barrier()
@@ -348,9 +366,12 @@ def run_native(args, cfg):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = t.item()
     e2e = {"value": world * B * Ke / dt, "unit": "clouds/s", "h2d_bytes_per_step": hs[0].h2d_bytes,
-           "d2h_bytes_per_step": hs[0].d2h_bytes, "ms_per_step": dt / Ke * 1e3,
-           "how": "2 graph slots on 2 streams fed from pinned host buffers; loss read back every step; wall clock"}
+           "d2h_bytes_per_step": hs[0].d2h_bytes, "ms_per_step": dt / Ke * 1e3, "steps": Ke,
+           "pcie_gbs": (hs[0].h2d_bytes + hs[0].d2h_bytes) * Ke / dt / 1e9,
+           "how": f"{NSLOT} graph slots on {NSLOT} streams, each [1 H2D copy from pinned memory, the step, 1 D2H copy]; "
+                  "every step's loss read on the host; wall clock, max over ranks"}
 
+    _stage("e2e done")
     if rank == 0:
         peaks = {}
         try:
@@ -361,12 +382,26 @@ def run_native(args, cfg):
         hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
         fp32_peak = 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12  # TFLOP/s, non-tensor FP32
         bpc = steps[0].bytes_per_cloud()
-        evals = {"fps": (G - 1) * N, "knn_group": G * N, "chamfer_fused": 2 * M * k * k, "chamfer_fwd": 2 * M * k * k}
-        dom = max((n for n in per_kernel if n in bpc), key=lambda n: per_kernel[n])
-        ach = bpc[dom] * B / (per_kernel[dom] * 1e-6) / 1e9
+        evals = {"fps": (G - 1) * N, "knn_group": G * N, "chamfer_fused": 2 * M * k * k, "chamfer_fwd": 2 * M * k * k,
+                 "cloud_step": (G - 1) * N + G * N + M * k * k}
+        traffic = {}
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f).get(args.config, {})
+        except (OSError, ValueError):
+            pass
+        if steps[0].fused:
+            # the step IS one kernel: its average duration over the timed region is the step time (launches
+            # overlap tail-to-head under programmatic dependent launch); the isolated launch is in roofline_detail
+            dom, dom_us = "cloud_step", ms / K * 1e3
+        else:
+            dom = max((n for n in per_kernel if n in bpc), key=lambda n: per_kernel[n])
+            dom_us = per_kernel[dom]
+        ach = bpc[dom] * B / (dom_us * 1e-6) / 1e9
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
-                    "us_per_launch": per_kernel[dom]}
+                    "frac": ach / hbm_peak, "traffic": traffic.get(dom), "peak_source": peak_src,
+                    "us_per_launch": dom_us, "algorithmic_bytes_per_launch": bpc[dom] * B,
+                    "note": "latency/issue-bound at this size: one CTA per cloud, 63 dependent FPS rounds; see DESIGN.md"}
         detail = {}
         for n, us in per_kernel.items():
             d = {"us_per_launch": round(us, 3)}
@@ -379,7 +414,7 @@ def run_native(args, cfg):
             if n == "fps":
                 d["us_per_iteration"] = round(us / max(G - 1, 1), 4)
             detail[n] = d
-        step_bytes = sum(bpc.values()) * B
+        step_bytes = (bpc["cloud_step"] if steps[0].fused else sum(v for n, v in bpc.items() if n != "cloud_step")) * B
         cpu_base, _ = time_cpu(cfg, budget_s=12.0) if not args.no_cpu_baseline else ({"value": None, "unit": "clouds/s", "cores": 0, "kind": "port", "sample": "skipped"}, 0)
         line = {"metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -387,8 +422,9 @@ def run_native(args, cfg):
                 "config": {"workload": desc, "B_per_gpu": B, "N": N, "G": G, "k": k, "M": M,
                            "l2_policy": f"inputs larger than L2: ring of {ring} buffer sets x {per_set / 1e6:.1f} MB",
                            "cuda_graph": True,
-                           "step_overlap": (f"programmatic dependent launch inside one graph of {ring} steps" if ring_graph is not None else "none"),
-                           "kernels_per_step": steps[0].kernels_per_step, "collective": ("in-graph" if collective_in_graph else "eager") if world > 1 else "none"},
+                           "step_overlap": (f"programmatic dependent launch inside graphs of up to {ring} steps"
+                                            if overlap and steps[0].fused else "none"),
+                           "kernels_per_step": steps[0].kernels_per_step, "collective": collective},
                 "clocks": clk, "e2e": e2e, "gpu_launches": steps[0].kernels_per_step * K,
                 "roofline": roofline, "roofline_detail": detail,
                 "step_hbm": {"algorithmic_bytes_per_step": step_bytes,
@@ -396,8 +432,13 @@ def run_native(args, cfg):
                 "cpu_baseline": cpu_base, "loss_check": losses[-1] if losses else None}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Captured NCCL work keeps the communicator busy at teardown (destroy_process_group / interpreter exit
+        # can hang on graphs that hold collectives): synchronise, flush and leave without running destructors.
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def _knn_group_only(L, s, st):

@@ -44,22 +44,36 @@ class GroupLossStep:
         self.seed, self.rand_offset = seed, rand_offset
         d, f32, i32 = self.dev, torch.float32, torch.int32
         e = lambda shape, dt: torch.empty(shape, dtype=dt, device=d)  # noqa: E731
-        # inputs
-        self.xyz = e((B, N, 3), f32)
-        self.loss_pred = e((B, G), f32)
-        self.pred = e((self.P, k, 3), f32)
+        # inputs: one arena [xyz | pred | loss_pred] so that a host-fed step needs ONE H2D copy
+        def carve(arena, specs):
+            views, o = [], 0
+            for shape, dt in specs:
+                n = int(torch.tensor(shape).prod().item()) * torch.empty((), dtype=dt).element_size()
+                views.append(arena[o:o + n].view(dt).view(shape))
+                o += (n + 255) & ~255
+            return views
+
+        def arena_bytes(specs):
+            return sum(((int(torch.tensor(sh).prod().item()) * torch.empty((), dtype=dt).element_size()) + 255) & ~255
+                       for sh, dt in specs)
+
+        self._in_specs = [((B, N, 3), f32), ((self.P, k, 3), f32), ((B, G), f32)]
+        self.in_arena = e((arena_bytes(self._in_specs),), torch.uint8)
+        self.xyz, self.pred, self.loss_pred = carve(self.in_arena, self._in_specs)
+        # results a host reads back every step: one arena [stats | per_patch | mask] = ONE D2H copy
+        self._res_specs = [((_lib.LOSS_STATS_LEN,), f32), ((self.P,), f32), ((B, G), torch.uint8)]
+        self.res_arena = e((arena_bytes(self._res_specs),), torch.uint8)
+        self.stats, self.per_patch, self.mask = carve(self.res_arena, self._res_specs)
+        self._carve = carve
         # outputs
         self.fps_idx = e((B, G), i32)
         self.center = e((B, G, 3), f32)
         self.neighborhood = e((B, G, k, 3), f32)
-        self.mask = e((B, G), torch.uint8)
         self.patch_index = e((self.P,), i32)
         self.dist1, self.dist2 = e((self.P, k), f32), e((self.P, k), f32)
         self.idx1, self.idx2 = e((self.P, k), i32), e((self.P, k), i32)
-        self.per_patch = e((self.P,), f32)
         self.total = e((1,), f32)
         self.grad_pred = e((self.P, k, 3), f32)
-        self.stats = e((_lib.LOSS_STATS_LEN,), f32)
         self.status = torch.zeros((1,), dtype=i32, device=d)
         ws = self.lib.gm3d_workspace_bytes(_lib.OP_GROUP, B, N, G, k)
         self.ws = e((ws,), torch.uint8) if ws else None
@@ -78,6 +92,10 @@ class GroupLossStep:
             # fused fwd+bwd: read pred + target patches once, write dist1/2 + idx1/2, per-patch loss, grad_pred
             "chamfer_fused": 24 * M * k + 16 * M * k + 4 * M + 12 * M * k,
             "hard_mask": 5 * G + 4 * M,
+            # the fused step reads xyz, loss_pred, pred once and writes every output once; the neighbourhood,
+            # centres and mask never come back from HBM
+            "cloud_step": 12 * N + 4 * G + 12 * M * k + (4 * G + 12 * G + 12 * G * k) + (G + 4 * M)
+                          + (16 * M * k + 4 * M + 12 * M * k),
         }
 
     def enqueue(self, flags: int = 0) -> None:
@@ -142,11 +160,18 @@ class GroupLossStep:
 class StepRing:
     """A ring of GroupLossStep buffer sets replayed as ONE CUDA graph.  The steps share no buffer, so the fused
     kernels are chained with programmatic dependent launch: step i+1 starts filling SMs while step i drains
-    (launch latency, the cold-cloud prologue and the last-CTA loss reduction of one step hide under the next)."""
+    (launch latency, the cold-cloud prologue and the last-CTA loss reduction of one step hide under the next).
 
-    def __init__(self, steps):
+    `reduce_stats`: when the process group has more than one rank, the [sum, sum_sq, count] heads of all the
+    ring's statistics vectors are packed into `self.head` (n, 3) and SUM-all-reduced ONCE per replay -- the
+    reference all-reduces its loss scalars only to log them (util/misc.py:345-353), so batching the ring's
+    scalars into one collective changes no result and keeps NCCL out of the kernel-to-kernel chain."""
+
+    def __init__(self, steps, reduce_stats: bool = False):
         self.steps = list(steps)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.reduce_stats = reduce_stats
+        self.head = torch.zeros((len(self.steps), 3), dtype=torch.float32, device=self.steps[0].dev) if reduce_stats else None
 
     def enqueue(self) -> None:
         n = len(self.steps)
@@ -155,6 +180,10 @@ class StepRing:
             if s.fused and n > 1:
                 f = (_lib.STEP_OVERLAP_NEXT if i + 1 < n else 0) | (_lib.STEP_OVERLAP_PREV if i > 0 else 0)
             s.enqueue(f)
+        if self.reduce_stats:
+            import torch.distributed as dist
+            torch.stack([s.stats[:3] for s in self.steps], out=self.head)
+            dist.all_reduce(self.head)
 
     def capture(self) -> "StepRing":
         dev = self.steps[0].dev
@@ -180,28 +209,26 @@ class StepRing:
 
 class HostStagedStep(GroupLossStep):
     """GroupLossStep fed from / drained to pinned host memory: the caller writes `h_xyz`, `h_pred`,
-    `h_loss_pred`, calls run(), and after a stream sync reads `h_stats` (loss scalars), `h_per_patch`
-    (the (B,M) loss matrix the loss predictor is trained on) and `h_mask`.  Copies are part of the graph."""
+    `h_loss_pred` (views of one pinned arena), calls run(), and after a stream sync reads `h_stats` (loss
+    scalars), `h_per_patch` (the (B,M) loss matrix the loss predictor is trained on) and `h_mask`.  One H2D
+    copy, the step, one D2H copy -- all three part of the captured graph."""
 
     def __init__(self, *a, **kw):
         super().__init__(*a, **kw)
-        pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # noqa: E731
-        self.h_xyz, self.h_pred, self.h_loss_pred = pin(self.xyz), pin(self.pred), pin(self.loss_pred)
-        self.h_stats, self.h_per_patch, self.h_mask = pin(self.stats), pin(self.per_patch), pin(self.mask)
+        self.h_in = torch.empty(self.in_arena.shape, dtype=torch.uint8, pin_memory=True)
+        self.h_res = torch.empty(self.res_arena.shape, dtype=torch.uint8, pin_memory=True)
+        self.h_xyz, self.h_pred, self.h_loss_pred = self._carve(self.h_in, self._in_specs)
+        self.h_stats, self.h_per_patch, self.h_mask = self._carve(self.h_res, self._res_specs)
 
     @property
     def h2d_bytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in (self.h_xyz, self.h_pred, self.h_loss_pred))
+        return self.h_in.numel()
 
     @property
     def d2h_bytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in (self.h_stats, self.h_per_patch, self.h_mask))
+        return self.h_res.numel()
 
-    def enqueue(self) -> None:
-        self.xyz.copy_(self.h_xyz, non_blocking=True)
-        self.pred.copy_(self.h_pred, non_blocking=True)
-        self.loss_pred.copy_(self.h_loss_pred, non_blocking=True)
-        super().enqueue()
-        self.h_stats.copy_(self.stats, non_blocking=True)
-        self.h_per_patch.copy_(self.per_patch, non_blocking=True)
-        self.h_mask.copy_(self.mask, non_blocking=True)
+    def enqueue(self, flags: int = 0) -> None:
+        self.in_arena.copy_(self.h_in, non_blocking=True)
+        super().enqueue(flags)
+        self.h_res.copy_(self.res_arena, non_blocking=True)
