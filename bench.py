@@ -163,7 +163,7 @@ def run_native(args, cfg):
     import torch.distributed as dist
 
     from gm3d_b200 import _lib
-    from gm3d_b200.pipeline import GroupLossStep, HostStagedStep, StepRing
+    from gm3d_b200.pipeline import GroupLossStep, HostStagedGroup, HostStagedStep, StepRing
 
     _lib.load()  # fail loudly if the CUDA library is missing
     if not torch.cuda.is_available():
@@ -321,42 +321,40 @@ def run_native(args, cfg):
 
     _stage("e2e")
     # ---- end-to-end: every step fed from pinned host memory, results read back
-    NSLOT = 4
-    hs = [HostStagedStep(B, N, G, k, ratio, device=dev, seed=1234, rand_offset=r * B * G) for r in range(NSLOT)]
-    for r, s in enumerate(hs):
-        x, lp, pred = synthetic_batch(B, N, G, k, M, 4321 + 1000 * rank + r)
-        s.h_xyz.copy_(torch.from_numpy(x)); s.h_pred.copy_(torch.from_numpy(pred)); s.h_loss_pred.copy_(torch.from_numpy(lp))
-    streams = [torch.cuda.Stream(dev) for _ in range(NSLOT)]
-    for s, strm in zip(hs, streams):
-        with torch.cuda.stream(strm):
-            s.capture(None)
+    # NGROUP graphs in flight on NGROUP streams, each = SUB x [H2D copy, the step, D2H copy]
+    NGROUP, SUB = int(os.environ.get("GM3D_E2E_GROUPS", "6")), int(os.environ.get("GM3D_E2E_SUB", "4"))
+    groups = []
+    for gi in range(NGROUP):
+        sub = []
+        for r in range(SUB):
+            s = HostStagedStep(B, N, G, k, ratio, device=dev, seed=1234, rand_offset=(gi * SUB + r) * B * G)
+            x, lp, pred = synthetic_batch(B, N, G, k, M, 4321 + 1000 * rank + gi * SUB + r)
+            s.h_xyz.copy_(torch.from_numpy(x)); s.h_pred.copy_(torch.from_numpy(pred)); s.h_loss_pred.copy_(torch.from_numpy(lp))
+            sub.append(s)
+        groups.append(HostStagedGroup(sub).capture())
     torch.cuda.synchronize()
-    Ke = max(K, 240)  # the host-fed pipeline needs a few hundred steps to reach steady state
+    hs = [groups[0].steps[0]]
+    Ke = -(-max(K, 240) // SUB) * SUB  # the host-fed pipeline needs a few hundred steps to reach steady state
     losses = []
 
     def e2e_steps(n):
-        # NSLOT slots on NSLOT streams, each slot's graph = [one H2D copy, the step, one D2H copy]: the copies of
-        # one step overlap the kernels of the others; the host reads a slot's loss (pinned h_stats) before it
-        # re-uses the slot, i.e. every step's result reaches the host inside the timed region
-        pending = [None] * NSLOT
-        for i in range(n):
-            j = i % NSLOT
-            if pending[j] is not None:
-                pending[j].synchronize()
-                losses.append(float(hs[j].h_stats[0]))
-            with torch.cuda.stream(streams[j]):
-                hs[j].run()
-                ev = torch.cuda.Event()
-                ev.record()
-            pending[j] = ev
-        for j in range(NSLOT):
-            jj = (n + j) % NSLOT
-            if pending[jj] is not None:
-                pending[jj].synchronize()
-                losses.append(float(hs[jj].h_stats[0]))
+        # every step's inputs cross PCIe from pinned memory and its loss / per-patch matrix / mask come back;
+        # the host reads the losses of a group before it re-launches that group
+        busy = [False] * NGROUP
+        for i in range(n // SUB):
+            j = i % NGROUP
+            if busy[j]:
+                losses.extend(groups[j].losses())
+            groups[j].launch()
+            busy[j] = True
+        for j in range(NGROUP):
+            jj = (n // SUB + j) % NGROUP
+            if busy[jj]:
+                losses.extend(groups[jj].losses())
 
-    e2e_steps(W)
+    e2e_steps(NGROUP * SUB * 2)
     barrier()
+    losses.clear()
     t0 = time.perf_counter()
     e2e_steps(Ke)
     torch.cuda.synchronize()
@@ -368,8 +366,9 @@ def run_native(args, cfg):
     e2e = {"value": world * B * Ke / dt, "unit": "clouds/s", "h2d_bytes_per_step": hs[0].h2d_bytes,
            "d2h_bytes_per_step": hs[0].d2h_bytes, "ms_per_step": dt / Ke * 1e3, "steps": Ke,
            "pcie_gbs": (hs[0].h2d_bytes + hs[0].d2h_bytes) * Ke / dt / 1e9,
-           "how": f"{NSLOT} graph slots on {NSLOT} streams, each [1 H2D copy from pinned memory, the step, 1 D2H copy]; "
-                  "every step's loss read on the host; wall clock, max over ranks"}
+           "losses_read": len(losses),
+           "how": f"{NGROUP} graphs in flight on {NGROUP} streams, each {SUB} x [1 H2D copy from pinned memory, the step, "
+                  "1 D2H copy]; every step's loss read on the host; wall clock, max over ranks"}
 
     _stage("e2e done")
     if rank == 0:

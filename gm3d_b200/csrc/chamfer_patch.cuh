@@ -88,7 +88,10 @@ __device__ __forceinline__ ChamferWarpOut chamfer_patch_warp(float ax, float ay,
         s1 += __shfl_xor_sync(kFull, s1, off);
         s2 += __shfl_xor_sync(kFull, s2, off);
     }
-    const float v = s1 / static_cast<float>(k) + s2 / static_cast<float>(k);
+    // mean over the k points; for a power-of-two k the division is an exact scaling, so the multiply is bit-identical
+    const float kf = static_cast<float>(k);
+    const float v = (k & (k - 1)) == 0 ? __fadd_rn(__fmul_rn(s1, 1.0f / kf), __fmul_rn(s2, 1.0f / kf))
+                                       : __fadd_rn(__fdiv_rn(s1, kf), __fdiv_rn(s2, kf));
     o.per_patch = norm == 1 ? 0.5f * v : v;
 
     // backward of the mean: upstream gradient gscale (L2) or gscale * 0.5 / sqrt(d) (L1); g = 2 * that

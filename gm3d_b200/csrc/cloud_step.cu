@@ -2,12 +2,12 @@
 // path is per-cloud work, so a persistent, warp-specialised CTA keeps the cloud in shared memory from the
 // first byte read to the last gradient written and no intermediate ever returns to HBM.
 //
-//   warps 0..7   "sampler": farthest-point sampling.  The cloud arrives by one 1-D bulk copy (TMA engine),
+//   warps 0..FW-1 "sampler" (FW = 4 for N <= 1024, else 8): farthest-point sampling.  The cloud arrives by one 1-D bulk copy (TMA engine),
 //                is transposed to structure-of-arrays in shared memory (the layout knn_select.cuh scans),
 //                points + running-min distances live in registers, packed FP32x2 distance updates, one
 //                named barrier per round (the other warps never take part in it).  Each selected centre
 //                is published through s_sel[] the moment it is known.
-//   warps 8..    "workers": pull patch ids g = 0, 1, ... from a shared counter, wait until centre g is
+//   warps FW..   "workers": pull patch ids g = 0, 1, ... from a shared counter, wait until centre g is
 //                published, select its k nearest points (knn_select.cuh), write the centred neighbourhood,
 //                and -- if patch g is masked -- run Chamfer forward + backward of that patch against the
 //                prediction (chamfer_patch.cuh) while the target patch is still in registers.
@@ -32,8 +32,7 @@
 
 namespace gm3d {
 
-constexpr int kCsFpsWarps = 8;
-constexpr int kCsFpsThreads = kCsFpsWarps * 32;
+constexpr int kCsMaxFpsWarps = 8;
 
 struct CloudStepParams {
     const float* xyz;
@@ -59,13 +58,14 @@ struct CloudStepParams {
     unsigned* ticket;
     int use_bulk;
     int flags;     // GM3D_STEP_* bits
+    unsigned long long* trace;  // tuning aid (GM3D_CS_TRACE = device pointer): per-CTA clock64 stamps, 64 words each
     int dbg_mode;  // tuning aid (GM3D_CS_MODE): 1 = sampler only, 2 = no loss work, 3 = prologue/epilogue only
     int npad;  // SoA length per coordinate: max(1024, N rounded up to 128)
     int LP;    // G rounded up to a power of two (>= 64)
 };
 
 struct CloudStepSmem {  // offsets into dynamic shared memory
-    size_t sx, sy, sz, aos, sel, cand, cham, key, msel, mrank, total;
+    size_t sx, sy, sz, aos, sel, ready, cand, cham, key, msel, mrank, total;
 };
 
 __host__ __device__ inline CloudStepSmem cloud_step_layout(int N, int G, int npad, int LP, int warps, bool loss) {
@@ -81,6 +81,7 @@ __host__ __device__ inline CloudStepSmem cloud_step_layout(int N, int G, int npa
     L.sz = take(static_cast<size_t>(npad) * 4);
     L.aos = take(static_cast<size_t>((N + 3) & ~3) * 12);
     L.sel = take(static_cast<size_t>(G) * 4);
+    L.ready = take(static_cast<size_t>(G) * 8);  // one mbarrier per centre: phase 0 completes when it is published
     L.cand = take(static_cast<size_t>(warps) * 64 * 8);
     L.cham = loss ? take(static_cast<size_t>(warps) * sizeof(ChamferWarpScratch)) : 0;
     L.key = (loss && LP > 64) ? take(static_cast<size_t>(LP) * 8) : 0;
@@ -90,7 +91,8 @@ __host__ __device__ inline CloudStepSmem cloud_step_layout(int N, int G, int npa
     return L;
 }
 
-__device__ __forceinline__ void fps_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kCsFpsThreads) : "memory"); }
+template <int THREADS>
+__device__ __forceinline__ void fps_bar() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 __device__ __forceinline__ int ld_volatile_s32(const int* p) {
     int v;
     asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
@@ -109,10 +111,11 @@ static __device__ __noinline__ void hard_mask_row_cold(const float* lrow, int L,
     hard_mask_row(lrow, L, LP, len_keep, len_loss, rrow, seed, ctr, row_id, mrow, prow, s_key, s_sel, lane, 32, SyncWarp());
 }
 
-template <int PPT, int WARPS, bool LOSS>
+template <int FW, int PPT, int WARPS, bool LOSS>
 __global__ void __launch_bounds__(WARPS * 32, 1) cloud_step_kernel(const __grid_constant__ CloudStepParams p) {
+    constexpr int kCsFpsWarps = FW, kCsFpsThreads = FW * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int2 s_red[2][kCsFpsWarps];
+    __shared__ int2 s_red[2][kCsMaxFpsWarps];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_mask_ready;  // 1 once s_msel / s_mrank are valid
 
@@ -126,23 +129,41 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cloud_step_kernel(const __grid_
     float* sz = reinterpret_cast<float*>(smem_raw + L.sz);
     float* s_aos = reinterpret_cast<float*>(smem_raw + L.aos);
     int* s_sel = reinterpret_cast<int*>(smem_raw + L.sel);
+    uint64_t* s_ready = reinterpret_cast<uint64_t*>(smem_raw + L.ready);
     uint8_t* s_msel = reinterpret_cast<uint8_t*>(smem_raw + L.msel);
     short* s_mrank = reinterpret_cast<short*>(smem_raw + L.mrank);
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // Roles: sampler warps 0..FW-1 (one per SM sub-partition when FW = 4), the rest are workers; the last worker
+    // first computes the cloud's mask.  (Measured alternatives, both slower: all sampler warps on ONE
+    // sub-partition with no worker next to them -- the chain then queues behind itself; and a single sampler
+    // warp with 32 points per lane -- 670 cycles per round.  Sharing sub-partitions costs the chain about 2x
+    // its stand-alone latency, but the workers' issue slots are what bounds the CTA.)
+    const bool is_fps = warp < FW;
+    const int ftid = tid;  // sampler thread index
+    const bool is_worker = warp >= FW;
+    const int nworkers = WARPS - FW;
+    const int wi = warp - FW;
+    const bool is_mask_warp = LOSS && warp == WARPS - 1;
     const float* cloud = p.xyz + static_cast<size_t>(b) * N * 3;
     const int M = G - p.len_keep;
+    unsigned long long* tr = p.trace ? p.trace + static_cast<size_t>(b) * 64 : nullptr;
+    if (tr && tid == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        tr[0] = clock64(), tr[60] = gt;
+    }
 
     // ---------------- prologue: cloud -> shared memory (AoS landing zone -> SoA), flags
-    if (p.use_bulk) {
-        if (tid == 0) {
-            mbar_init(&s_bar, 1);
-            mbar_fence_init();
-        }
+    if (tid == 0) mbar_init(&s_bar, 1);
+    for (int g = tid; g < G; g += WARPS * 32) {
+        s_sel[g] = 0;  // FPS starts at point 0
+        mbar_init(&s_ready[g], 1);
     }
-    for (int g = tid; g < G; g += WARPS * 32) s_sel[g] = g == 0 ? 0 : -1;  // FPS starts at point 0
     if (tid == 0) s_mask_ready = 0;
+    mbar_fence_init();
     __syncthreads();
+    if (tid == 0) mbar_arrive(&s_ready[0]);  // centre 0 is point 0: known from the start
     if (p.use_bulk) {
         if (tid == 0) {
             const uint32_t bytes = static_cast<uint32_t>(N) * 12u;
@@ -151,23 +172,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cloud_step_kernel(const __grid_
         }
     }
 
-    // 32-warp variant: the launch gives every thread 64 registers; the two sampler warpgroups release down to
-    // 40 and the six worker warpgroups take 72 (8*32*40 + 24*32*72 = 65536 = the whole register file).
-    if (WARPS == 32) {
-        if (warp < kCsFpsWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        else asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");
-    }
     float2 X[PPT / 2], Y[PPT / 2], Z[PPT / 2], T[PPT / 2];
-    if (warp < kCsFpsWarps) {
+    if (is_fps) {
         if (p.use_bulk) mbar_wait(&s_bar, 0);
         const float* src = p.use_bulk ? s_aos : cloud;
 #pragma unroll
         for (int s = 0; s < PPT; ++s) {
-            const int i = s * kCsFpsThreads + tid;
+            const int i = s * kCsFpsThreads + ftid;
             float x = 0.f, y = 0.f, z = 0.f, t = -1.0f;  // min(d, -1) stays -1: a slot past N is never selected
             if (i < N) {
                 x = src[3 * i + 0], y = src[3 * i + 1], z = src[3 * i + 2];
                 sx[i] = x, sy[i] = y, sz[i] = z;
+                if (!p.use_bulk) s_aos[3 * i] = x, s_aos[3 * i + 1] = y, s_aos[3 * i + 2] = z;
                 // pointnet2: `if (mag <= 1e-3) continue;` with a double literal => double compare
                 t = (static_cast<double>(sumsq_nvcc(x, y, z)) <= 1e-3) ? -1.0f : 1e10f;
             }
@@ -175,15 +191,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cloud_step_kernel(const __grid_
             else X[s >> 1].x = x, Y[s >> 1].x = y, Z[s >> 1].x = z, T[s >> 1].x = t;
         }
         const float inf = __uint_as_float(kInfBits);
-        for (int i = N + tid; i < p.npad; i += kCsFpsThreads) sx[i] = inf, sy[i] = inf, sz[i] = inf;
+        for (int i = N + ftid; i < p.npad; i += kCsFpsThreads) sx[i] = inf, sy[i] = inf, sz[i] = inf;
     }
     __syncthreads();  // SoA cloud visible to every warp
+    if (tr && tid == 0) tr[1] = clock64();
 
-    if (warp < kCsFpsWarps) {
-        // ---------------- sampler: G - 1 dependent rounds
+    if (is_fps) {
+        // ---------------- sampler warps: G - 1 dependent rounds
         int old = 0;
-        for (int j = 1; j < (p.dbg_mode == 3 ? 1 : G); ++j) {
-            const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
+        const int rounds = p.dbg_mode == 3 ? 1 : G;
+        const int2* red_rd = &s_red[0][lane & (FW - 1)];  // every lane re-reduces the FW warp results (duplicates are harmless)
+        for (int j = 1; j < rounds; ++j) {
+            const float* w = s_aos + 3 * old;  // winner of the previous round (AoS copy: one address, three loads)
+            const float x1 = w[0], y1 = w[1], z1 = w[2];
             const float2 x2 = make_float2(x1, x1), y2 = make_float2(y1, y1), z2 = make_float2(z1, z1);
             float m[PPT];
 #pragma unroll
@@ -193,38 +213,42 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cloud_step_kernel(const __grid_
                 T[h].y = fminf(d.y, T[h].y);
                 m[2 * h] = T[h].x, m[2 * h + 1] = T[h].y;
             }
-            // thread arg-max, lowest slot on ties (slot s <-> point s * 256 + tid): pairwise tournament
+            // thread arg-max, lowest slot on ties (slot s <-> point s * FT + tid): pairwise tournament
             int mi[PPT];
 #pragma unroll
             for (int s = 0; s < PPT; ++s) mi[s] = s;
 #pragma unroll
-            for (int w = 1; w < PPT; w <<= 1) {
+            for (int ww = 1; ww < PPT; ww <<= 1) {
 #pragma unroll
-                for (int s = 0; s < PPT; s += 2 * w) {
-                    const bool hi = m[s + w] > m[s];
-                    m[s] = hi ? m[s + w] : m[s];
-                    mi[s] = hi ? mi[s + w] : mi[s];
+                for (int s = 0; s < PPT; s += 2 * ww) {
+                    const bool hi = m[s + ww] > m[s];
+                    m[s] = hi ? m[s + ww] : m[s];
+                    mi[s] = hi ? mi[s + ww] : mi[s];
                 }
             }
             const int v = f2ord(m[0]);
-            const int besti = mi[0] * kCsFpsThreads + tid;
+            const int besti = mi[0] * kCsFpsThreads + ftid;
             const int vmax = __reduce_max_sync(kFull, v);
             const int kmin = __reduce_min_sync(kFull, v == vmax ? besti : INT_MAX);
             if (lane == 0) s_red[j & 1][warp] = make_int2(vmax, kmin);
-            fps_bar();
-            const int2 r = lane < kCsFpsWarps ? s_red[j & 1][lane] : make_int2(INT_MIN, INT_MAX);
+            fps_bar<kCsFpsThreads>();
+            const int2 r = red_rd[(j & 1) * kCsMaxFpsWarps];
             const int gmax = __reduce_max_sync(kFull, r.x);
             old = __reduce_min_sync(kFull, r.x == gmax ? r.y : INT_MAX);
-            if (tid == 0) st_volatile_s32(&s_sel[j], old);  // publishes centre j to the workers
+            if (ftid == 0) {  // publish centre j: the arrive releases the store, a worker's wait acquires it
+                s_sel[j] = old;
+                mbar_arrive(&s_ready[j]);
+            }
         }
-        fps_bar();
-        for (int g = tid; g < G; g += kCsFpsThreads) {
+        if (tr && ftid == 0) tr[2] = clock64();
+        fps_bar<kCsFpsThreads>();
+        for (int g = ftid; g < G; g += kCsFpsThreads) {
             const int i = s_sel[g];
             p.fps_idx[static_cast<size_t>(b) * G + g] = i;
             float* c = p.centers + (static_cast<size_t>(b) * G + g) * 3;
             c[0] = sx[i], c[1] = sy[i], c[2] = sz[i];
         }
-    } else if (LOSS && warp == WARPS - 1) {
+    } else if (is_mask_warp) {
         // ---------------- the cloud's hard-patch mask (needs loss_pred only), then the masked rank of each patch
         const float* lrow = p.loss_pred ? p.loss_pred + static_cast<size_t>(b) * G : nullptr;
         const float* rrow = p.rand_keys ? p.rand_keys + static_cast<size_t>(b) * G : nullptr;
@@ -252,14 +276,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cloud_step_kernel(const __grid_
     }
 
     // ---------------- workers: patch g = worker, worker + #workers, ... (centres appear in that order)
-    if (warp >= kCsFpsWarps) {
+    if (is_worker) {
         u64* cb = reinterpret_cast<u64*>(smem_raw + L.cand) + warp * 64;
         ChamferWarpScratch* csc = LOSS ? reinterpret_cast<ChamferWarpScratch*>(smem_raw + L.cham) + warp : nullptr;
         const int nf = 3 * k;  // floats per patch
-        for (int g = warp - kCsFpsWarps; g < G; g += WARPS - kCsFpsWarps) {
+        for (int g = wi; g < G; g += nworkers) {
             if (p.dbg_mode == 1 || p.dbg_mode == 3) break;
-            int c;
-            while ((c = ld_volatile_s32(&s_sel[g])) < 0) __nanosleep(64);
+            const long long w0 = tr ? clock64() : 0;
+            mbar_wait(&s_ready[g], 0);  // suspended in hardware until centre g is published: no polling instructions
+            const int c = s_sel[g];
+            if (tr && lane == 0) tr[32 + warp] += clock64() - w0;
             const float qx = sx[c], qy = sy[c], qz = sz[c];
             u64 top;
             float thr;
@@ -288,15 +314,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cloud_step_kernel(const __grid_
                 const int mr = s_mrank[g];
                 if (mr >= 0) {  // warp-uniform: patch g is masked, its prediction is row b*M + mr
                     const size_t pp = static_cast<size_t>(b) * M + mr;
+                    const size_t pe = pp * k + lane;  // element (patch, lane) of the (P, k) outputs
                     const float* pa = p.pred + pp * nf + 3 * (lane < k ? lane : 0);
                     const float ax = __ldg(pa), ay = __ldg(pa + 1), az = __ldg(pa + 2);
                     const ChamferWarpOut o = chamfer_patch_warp(ax, ay, az, bx, by, bz, k, p.norm, p.gscale1, p.gscale2, lane, csc);
                     if (lane < k) {
-                        if (p.dist1) p.dist1[pp * k + lane] = o.dist1;
-                        if (p.dist2) p.dist2[pp * k + lane] = o.dist2;
-                        if (p.idx1) p.idx1[pp * k + lane] = o.idx1;
-                        if (p.idx2) p.idx2[pp * k + lane] = o.idx2;
-                        float* go = p.gxyz1 + pp * nf + 3 * lane;
+                        if (p.dist1) p.dist1[pe] = o.dist1;
+                        if (p.dist2) p.dist2[pe] = o.dist2;
+                        if (p.idx1) p.idx1[pe] = o.idx1;
+                        if (p.idx2) p.idx2[pe] = o.idx2;
+                        float* go = p.gxyz1 + pe * 3;
                         go[0] = o.gx, go[1] = o.gy, go[2] = o.gz;
                     }
                     if (lane == 0 && p.per_patch) p.per_patch[pp] = o.per_patch;
@@ -305,6 +332,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cloud_step_kernel(const __grid_
         }
     }
 
+    if (tr && lane == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        tr[4 + warp] = clock64(), tr[61] = gt;  // (any warp's end stamp; they finish within a few us of each other)
+    }
     if (LOSS && p.ticket) {
         if (last_cta(p.ticket)) final_loss_reduce_cold(p.per_patch, p.B * M, p.total, p.stats);
     }
@@ -312,9 +344,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cloud_step_kernel(const __grid_
 
 size_t cloud_step_workspace_bytes(int P) { return P > 0 ? 16 + static_cast<size_t>(P) * sizeof(float) : 0; }
 
-template <int PPT, int WARPS, bool LOSS>
+template <int FW, int PPT, int WARPS, bool LOSS>
 static int launch_cloud_step(const CloudStepParams& p, size_t smem, cudaStream_t st) {
-    auto kern = cloud_step_kernel<PPT, WARPS, LOSS>;
+    auto kern = cloud_step_kernel<FW, PPT, WARPS, LOSS>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return static_cast<int>(e);
@@ -330,10 +362,10 @@ static int launch_cloud_step(const CloudStepParams& p, size_t smem, cudaStream_t
     return e == cudaSuccess ? launch_status() : static_cast<int>(e);
 }
 
-constexpr int kCsWarps = 24;  // 8 sampler + 16 worker warps
+constexpr int kCsWarps = 24;  // sampler + worker warps (80 registers per thread)
 
-// Largest N the fused kernel serves: 8 points per sampler thread.
-constexpr int kCloudStepMaxN = kCsFpsThreads * 8;
+// Largest N the fused kernel serves: 8 sampler warps x 8 points per thread.
+constexpr int kCloudStepMaxN = kCsMaxFpsWarps * 32 * 8;
 
 bool cloud_step_supported(int N, int G, int k) { return N <= kCloudStepMaxN && G <= 1024 && k <= 32 && N >= 1 && G <= N; }
 
@@ -341,10 +373,12 @@ template <int WARPS>
 static int cloud_step_dispatch(CloudStepParams& p, bool loss, cudaStream_t st) {
     const CloudStepSmem L = cloud_step_layout(p.N, p.G, p.npad, p.LP, WARPS, loss);
     if (L.total > 200 * 1024) return GM3D_ENOSUP;
-    if (p.N <= kCsFpsThreads * 4) {
-        return loss ? launch_cloud_step<4, WARPS, true>(p, L.total, st) : launch_cloud_step<4, WARPS, false>(p, L.total, st);
+    // N <= 1024: four sampler warps (one per SM sub-partition) with 8 points per thread -- half the issue slots
+    // of eight warps x 4 points for the same chain, and four more workers; else eight sampler warps x 8 points
+    if (p.N <= 1024) {
+        return loss ? launch_cloud_step<4, 8, WARPS, true>(p, L.total, st) : launch_cloud_step<4, 8, WARPS, false>(p, L.total, st);
     }
-    return loss ? launch_cloud_step<8, WARPS, true>(p, L.total, st) : launch_cloud_step<8, WARPS, false>(p, L.total, st);
+    return loss ? launch_cloud_step<8, 8, WARPS, true>(p, L.total, st) : launch_cloud_step<8, 8, WARPS, false>(p, L.total, st);
 }
 
 int cloud_step_launch(CloudStepParams p, cudaStream_t st) {
@@ -357,11 +391,13 @@ int cloud_step_launch(CloudStepParams p, cudaStream_t st) {
     static const int warps = getenv("GM3D_CS_WARPS") ? atoi(getenv("GM3D_CS_WARPS")) : kCsWarps;
     static const int mode = getenv("GM3D_CS_MODE") ? atoi(getenv("GM3D_CS_MODE")) : 0;
     p.dbg_mode = mode;
+    static unsigned long long* const trace =
+        getenv("GM3D_CS_TRACE") ? reinterpret_cast<unsigned long long*>(strtoull(getenv("GM3D_CS_TRACE"), nullptr, 0)) : nullptr;
+    p.trace = trace;
     switch (warps) {
         case 12: return cloud_step_dispatch<12>(p, loss, st);
         case 16: return cloud_step_dispatch<16>(p, loss, st);
         case 20: return cloud_step_dispatch<20>(p, loss, st);
-        case 32: return cloud_step_dispatch<32>(p, loss, st);
         default: return cloud_step_dispatch<kCsWarps>(p, loss, st);
     }
 }

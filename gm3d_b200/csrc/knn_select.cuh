@@ -95,6 +95,23 @@ __device__ __forceinline__ unsigned sort_u32(unsigned v, int lane) {
     }
     return v;
 }
+// Two independent 32-lane ascending sorts at once: the low and the high 16-bit halves of v are sorted
+// separately across the lanes (VIMNMX.U16x2).
+__device__ __forceinline__ unsigned sort_u16x2(unsigned v, int lane) {
+#pragma unroll
+    for (int sz = 2; sz <= 32; sz <<= 1) {
+        {
+            const unsigned o = __shfl_xor_sync(kFull, v, sz - 1);
+            v = (lane & (sz >> 1)) == 0 ? __vminu2(v, o) : __vmaxu2(v, o);
+        }
+#pragma unroll
+        for (int st = sz >> 2; st > 0; st >>= 1) {
+            const unsigned o = __shfl_xor_sync(kFull, v, st);
+            v = (lane & st) == 0 ? __vminu2(v, o) : __vmaxu2(v, o);
+        }
+    }
+    return v;
+}
 __device__ __forceinline__ unsigned merge_u32(unsigned v, int lane) {  // bitonic -> ascending
 #pragma unroll
     for (int st = 16; st > 0; st >>= 1) {
@@ -165,12 +182,14 @@ __device__ __forceinline__ bool bootstrap_query(const float* __restrict__ sx, co
             ma = fminf(fminf(ma, d23.x), d23.y);
         }
     }
-    // T = k-th smallest of the 64 group minima (bit patterns of non-negative floats order like uints),
-    // clamped to FLT_MAX so that +inf padding never passes.
-    const unsigned a = sort_u32<32>(__float_as_uint(ma), lane);
-    const unsigned b2 = sort_u32<32>(__float_as_uint(mb), lane);
-    const unsigned rev = __shfl_sync(kFull, b2, 31 - lane);
-    unsigned low = min(a, rev);  // the 32 smallest of the 64, as a bitonic sequence
+    // T = an upper bound of the k-th smallest of the 64 group minima.  Only a bound is needed, so the minima are
+    // truncated to their upper 16 bits (sign, exponent, 7 mantissa bits: still order-preserving for
+    // non-negative floats) and BOTH lists are sorted by one packed network; the k-th smallest truncated value,
+    // filled up with ones, bounds every minimum that truncates to it.  Clamped to FLT_MAX so that +inf padding
+    // never passes.
+    const unsigned both = sort_u16x2(__byte_perm(__float_as_uint(ma), __float_as_uint(mb), 0x7632), lane);
+    const unsigned rev = __shfl_sync(kFull, both, 31 - lane);
+    unsigned low = min(both & 0xffffu, rev >> 16);  // the 32 smallest of the 64, as a bitonic sequence
     unsigned tb;
     if (k == 32) {
         tb = __reduce_max_sync(kFull, low);
@@ -178,10 +197,11 @@ __device__ __forceinline__ bool bootstrap_query(const float* __restrict__ sx, co
         low = merge_u32(low, lane);
         tb = __shfl_sync(kFull, low, k - 1);
     }
-    tb = min(tb, kFltMaxBits);
+    tb = min((tb << 16) | 0xffffu, kFltMaxBits);
     unsigned pm = 0;
 #pragma unroll
-    for (int s = 0; s < 32; ++s) pm |= __float_as_uint(d[s]) <= tb ? (1u << s) : 0u;
+    for (int s = 0; s < 32; ++s)  // one compare + one predicated OR per point
+        asm("{.reg .pred p; setp.le.u32 p, %1, %2; @p or.b32 %0, %0, %3;}" : "+r"(pm) : "r"(__float_as_uint(d[s])), "r"(tb), "r"(1u << s));
     const int mine = __popc(pm);
     int incl = mine;
 #pragma unroll
@@ -193,10 +213,19 @@ __device__ __forceinline__ bool bootstrap_query(const float* __restrict__ sx, co
     if (total > 64) return false;
     int off = incl - mine;
     unsigned short* cl = reinterpret_cast<unsigned short*>(cb);  // compacted tile-local indices of the passing points
-    while (pm) {  // ~1.4 passing points per lane
+    // ~1.4 passing points per lane: two branch-free extractions, then the rare longer tails
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
         const int s = __ffs(pm) - 1;
+        if (pm) cl[off] = static_cast<unsigned short>(((s >> 2) << 7) + (lane << 2) + (s & 3));
+        off += pm != 0;
         pm &= pm - 1;
-        cl[off++] = static_cast<unsigned short>(((s >> 2) << 7) + (lane << 2) + (s & 3));
+    }
+    while (__any_sync(kFull, pm != 0)) {
+        const int s = __ffs(pm) - 1;
+        if (pm) cl[off] = static_cast<unsigned short>(((s >> 2) << 7) + (lane << 2) + (s & 3));
+        off += pm != 0;
+        pm &= pm - 1;
     }
     __syncwarp();
     // ---- every lane re-evaluates up to two candidates (same expression => same bits as in the scan), the

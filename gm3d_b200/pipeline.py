@@ -232,3 +232,39 @@ class HostStagedStep(GroupLossStep):
         self.in_arena.copy_(self.h_in, non_blocking=True)
         super().enqueue(flags)
         self.h_res.copy_(self.res_arena, non_blocking=True)
+
+
+class HostStagedGroup:
+    """Several HostStagedStep slots replayed as ONE graph on one stream: [H2D, step, D2H] x n.  A host loop
+    that launches one graph per step is bound by Python / launch overhead long before PCIe; grouping a few
+    steps per launch and rotating two or three groups over separate streams keeps the copy engines and the
+    SMs busy at the same time.  After `done.synchronize()` every slot's pinned results are valid."""
+
+    def __init__(self, steps):
+        self.steps = list(steps)
+        self.stream = torch.cuda.Stream(self.steps[0].dev)
+        self.done = torch.cuda.Event()
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        # zero-copy NumPy views of the pinned statistics (reading a loss costs no torch dispatch)
+        self.h_stats_np = [s.h_stats.numpy() for s in self.steps]
+
+    def capture(self) -> "HostStagedGroup":
+        with torch.cuda.stream(self.stream):
+            for s in self.steps:
+                s.enqueue()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self.stream):
+            for s in self.steps:
+                s.enqueue()
+        self.graph = g
+        return self
+
+    def launch(self) -> None:
+        with torch.cuda.stream(self.stream):
+            self.graph.replay()
+            self.done.record()
+
+    def losses(self):
+        self.done.synchronize()
+        return [float(v[0]) for v in self.h_stats_np]

@@ -1,7 +1,13 @@
+# One GPU-box pass that produces everything a round is judged on (run through gpurun; outputs in gpurun_out/).
+#   bash tools/gpu_round_check.sh <tag>
+tag=${1:-rX}
 set -x
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_r1c.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_r1c.log
-python bench.py > gpurun_out/bench_r1c.json 2> gpurun_out/bench_r1c.err; echo "bench rc=$?"
-python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref_r1c.json 2> gpurun_out/bench_ref_r1c.err; echo "ref rc=$?"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_r1c.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_r1c.log 2>&1; echo "ncu launches rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:"fps_reg|knn_group|chamfer_small|hard_mask" -s 4 -c 4 -o gpurun_out/prof_c2_r1c python tools/prof_kernels.py --config c2 --reps 1 > gpurun_out/ncu_c2_r1c.log 2>&1; echo "ncu full rc=$?"
-python -c "import __graft_entry__ as g; g.smoke()"
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$tag.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_gpu_$tag.log
+timeout 600 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "bench rc=$?"
+timeout 600 python bench.py --no-overlap --no-cpu-baseline > gpurun_out/bench_nooverlap_$tag.json 2> gpurun_out/bench_nooverlap_$tag.err; echo "bench no-overlap rc=$?"
+timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref_$tag.json 2> gpurun_out/bench_ref_$tag.err; echo "ref rc=$?"
+# launch list of the same command (per-launch times are cold-cache and serialised: shares, not absolutes)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_$tag.csv python bench.py --steps 48 --warmup 24 --no-cpu-baseline > gpurun_out/ncu_launch_$tag.log 2>&1; echo "ncu launches rc=$?"
+# one full-set capture of the dominant kernel
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"cloud_step" -s 1 -c 1 -o gpurun_out/prof_cloud_step_$tag python tools/prof_kernels.py --config c2 --reps 2 --only cloud_step > gpurun_out/ncu_full_$tag.log 2>&1; echo "ncu full rc=$?"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()"
