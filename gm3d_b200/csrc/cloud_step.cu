@@ -112,7 +112,7 @@ static __device__ __noinline__ void hard_mask_row_cold(const float* lrow, int L,
 }
 
 template <int FW, int PPT, int WARPS, bool LOSS>
-__global__ void __launch_bounds__(WARPS * 32, 1) cloud_step_kernel(const __grid_constant__ CloudStepParams p) {
+__global__ void __launch_bounds__(WARPS * 32, WARPS <= 12 ? 2 : 1) cloud_step_kernel(const __grid_constant__ CloudStepParams p) {
     constexpr int kCsFpsWarps = FW, kCsFpsThreads = FW * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int2 s_red[2][kCsMaxFpsWarps];
@@ -388,7 +388,12 @@ int cloud_step_launch(CloudStepParams p, cudaStream_t st) {
     while (LP < p.G) LP <<= 1;
     p.LP = LP;
     p.use_bulk = (p.N % 4 == 0) && (reinterpret_cast<uintptr_t>(p.xyz) % 16 == 0);
-    static const int warps = getenv("GM3D_CS_WARPS") ? atoi(getenv("GM3D_CS_WARPS")) : kCsWarps;
+    // Overlapped steps (programmatic dependent launch) keep every SM supplied with CTAs of the next step, so two
+    // 12-warp CTAs per SM (two independent FPS chains in flight, 2 x 8 workers) beat one 24-warp CTA: the
+    // latency-bound chain of one cloud hides under the other cloud's work.  A lone step has one CTA per SM
+    // either way and wants all 20 workers.  GM3D_CS_WARPS overrides (tuning aid).
+    static const int env_warps = getenv("GM3D_CS_WARPS") ? atoi(getenv("GM3D_CS_WARPS")) : 0;
+    const int warps = env_warps ? env_warps : ((p.flags & (GM3D_STEP_OVERLAP_NEXT | GM3D_STEP_OVERLAP_PREV)) ? 12 : kCsWarps);
     static const int mode = getenv("GM3D_CS_MODE") ? atoi(getenv("GM3D_CS_MODE")) : 0;
     p.dbg_mode = mode;
     static unsigned long long* const trace =
