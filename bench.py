@@ -33,6 +33,9 @@ METRIC = "clouds/s FPS+kNN-group+Chamfer fwd/bwd"
 CONFIGS = {  # name: (B per GPU, N, G, k, mask_ratio, description)
     "c1": (8, 1024, 64, 32, 0.6, "Point-MAE Group+Chamfer-L2 B=8 N=1024 G=64 k=32"),
     "c2": (128, 1024, 64, 32, 0.6, "Point-MAE+GM3D pretrain B=128 N=1024 G=64 k=32 M=39 Chamfer-L2 fwd+bwd + hard-patch mask"),
+    "c3l0": (128, 2048, 512, 16, 0.8, "Point-M2AE+GM3D level 0: B=128 N=2048 G=512 k=16 M=410"),
+    "c3l1": (128, 512, 256, 8, 0.8, "Point-M2AE+GM3D level 1 (on level-0 centres): B=128 N=512 G=256 k=8 M=205"),
+    "c3l2": (128, 256, 64, 8, 0.8, "Point-M2AE+GM3D level 2 (on level-1 centres): B=128 N=256 G=64 k=8 M=52"),
     "c4": (32, 2048, 128, 32, 0.6, "ScanObjectNN finetune shape B=32 N=2048 G=128 k=32 (+loss for uniformity)"),
     "c5": (128, 8192, 512, 32, 0.6, "scaling sweep shard B=128/GPU N=8192 G=512 k=32 M=308"),
 }

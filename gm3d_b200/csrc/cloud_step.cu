@@ -393,7 +393,8 @@ int cloud_step_launch(CloudStepParams p, cudaStream_t st) {
     // latency-bound chain of one cloud hides under the other cloud's work.  A lone step has one CTA per SM
     // either way and wants all 20 workers.  GM3D_CS_WARPS overrides (tuning aid).
     static const int env_warps = getenv("GM3D_CS_WARPS") ? atoi(getenv("GM3D_CS_WARPS")) : 0;
-    const int warps = env_warps ? env_warps : ((p.flags & (GM3D_STEP_OVERLAP_NEXT | GM3D_STEP_OVERLAP_PREV)) ? 12 : kCsWarps);
+    const bool pair = (p.flags & (GM3D_STEP_OVERLAP_NEXT | GM3D_STEP_OVERLAP_PREV)) && p.N <= 1024;  // 4 sampler + 8 worker warps
+    const int warps = env_warps ? env_warps : (pair ? 12 : kCsWarps);
     static const int mode = getenv("GM3D_CS_MODE") ? atoi(getenv("GM3D_CS_MODE")) : 0;
     p.dbg_mode = mode;
     static unsigned long long* const trace =

@@ -186,7 +186,9 @@ GM3D_API int gm3d_group_f32(const float* xyz, int B, int N, int G, int k, int32_
     if (!xyz || !fps_idx || !centers || !nbhd || B <= 0 || N <= 0 || G <= 0 || k <= 0 || k > N || G > N)
         return GM3D_EINVAL;
     if (k > GM3D_KNN_MAX_K) return GM3D_ENOSUP;
-    if (N <= 2048 && G <= 1024)  // one CTA per cloud: sampling and patch selection overlapped (cloud_step.cu)
+    // One CTA per cloud with sampling and patch selection overlapped (cloud_step.cu) pays off when the batch
+    // fills most SMs and a cloud's selection work fits beside its FPS chain; otherwise two grid-wide kernels.
+    if (N <= 2048 && B >= 96 && static_cast<long long>(G) * ((N + 1023) / 1024) <= 256)
         return gm3d_cloud_step_f32(xyz, B, N, G, k, fps_idx, centers, knn_idx, nbhd, nbhd_org, nullptr, 0, 0, nullptr, 0, 0,
                                    nullptr, nullptr, nullptr, 0.f, 0.f, 2, nullptr, nullptr, nullptr, nullptr, nullptr,
                                    nullptr, nullptr, nullptr, 0, nullptr, stream);

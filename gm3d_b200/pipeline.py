@@ -32,7 +32,11 @@ class GroupLossStep:
         can_fuse = N <= FUSED_MAX_N and G <= FUSED_MAX_G and k <= _lib.KNN_MAX_K
         if fused and not can_fuse:
             raise NotImplementedError(f"gm3d_cloud_step_f32 serves N <= {FUSED_MAX_N}, G <= {FUSED_MAX_G}")
-        self.fused = can_fuse if fused is None else fused
+        # default: one CTA per cloud pays off when a cloud's selection work fits beside its FPS chain (measured on
+        # B200: C1, C2, C4, M2AE levels 1-2 yes -- small batches included, because overlapped steps share the
+        # GPU; M2AE level 0 with G=512 x 2 tiles no)
+        worth = G * ((N + 1023) // 1024) <= 256
+        self.fused = (can_fuse and worth) if fused is None else fused
         self.kernels_per_step = 1 if self.fused else KERNELS_PER_STEP
         self.dev = torch.device(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
         if self.dev.type != "cuda":

@@ -540,6 +540,8 @@ def test_cloud_step_rejects_unsupported(cuda):
         GroupLossStep(2, 4096, 64, 32, device=cuda, fused=True)
     s = GroupLossStep(2, 4096, 64, 32, device=cuda)  # falls back to the kernel sequence by itself
     assert not s.fused
+    assert GroupLossStep(128, 1024, 64, 32, device=cuda).fused          # BASELINE config[1]
+    assert not GroupLossStep(128, 2048, 512, 16, device=cuda).fused     # M2AE level 0: too much selection work per CTA
     lib = _lib.load()
     p = s.xyz.data_ptr()
     assert lib.gm3d_cloud_step_f32(p, 2, 4096, 64, 32, p, p, None, p, None, None, 0, 0, None, 0, 0, None, None, None,
@@ -554,7 +556,7 @@ def test_step_ring_overlapped_steps_equal_serial_steps(cuda):
     rng = np.random.default_rng(9)
     steps, want = [], []
     for r in range(6):
-        s = GroupLossStep(B, N, G, k, 0.6, device=cuda, seed=4, rand_offset=r * B * G)
+        s = GroupLossStep(B, N, G, k, 0.6, device=cuda, seed=4, rand_offset=r * B * G, fused=True)
         s.xyz.copy_(dev(synthetic_clouds(B, N, 300 + r), cuda))
         s.loss_pred.copy_(dev(rng.standard_normal((B, G)).astype(np.float32), cuda))
         s.pred.copy_(dev((rng.standard_normal((s.P, k, 3)) * 0.08).astype(np.float32), cuda))
