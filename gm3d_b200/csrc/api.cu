@@ -5,6 +5,7 @@ namespace gm3d {
 size_t fps_workspace_bytes(int B, int N);
 size_t chamfer_workspace_bytes(int P);
 size_t cloud_step_workspace_bytes(int P);
+size_t learning_loss_workspace_bytes(int B);
 }
 
 GM3D_API int gm3d_abi_version(void) { return GM3D_ABI_VERSION; }
@@ -29,6 +30,7 @@ GM3D_API size_t gm3d_workspace_bytes(int op, int B, int N, int G, int k) {
         case GM3D_OP_GROUP: return gm3d::fps_workspace_bytes(B, N);
         case GM3D_OP_CHAMFER_FWD: return gm3d::chamfer_workspace_bytes(B);  // ticket + per-patch scratch
         case GM3D_OP_CLOUD_STEP: return gm3d::cloud_step_workspace_bytes(B);
+        case GM3D_OP_LEARNING_LOSS: return gm3d::learning_loss_workspace_bytes(B);
         default: return 0;
     }
 }

@@ -85,3 +85,29 @@ def forward_loss_feature(pred: torch.Tensor, target: torch.Tensor, mask: torch.T
     loss_chamfer = _MaskedChamfer.apply(rec, pool, index, 2, per_point)
     loss_chamfer = loss_chamfer.reshape(N, PP, -1).mean(-1)
     return {"MSE_mean": loss_mse.mean(), "Chamfer_mean": loss_chamfer.mean(), "matrix": loss_mse + loss_chamfer}
+
+
+class _LearningLoss(torch.autograd.Function):
+    """value + gradient w.r.t. loss_pred from ONE launch (the kernel that forms the pairwise terms also emits
+    their derivatives; backward only scales by the upstream scalar)."""
+
+    @staticmethod
+    def forward(ctx, loss_pred, loss_target, relative):
+        loss, grad = ops.learning_loss(loss_pred, loss_target, relative, 1.0, want_grad=loss_pred.requires_grad)
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return (grad * g if grad is not None else None), None, None
+
+
+def forward_learning_loss(loss_pred: torch.Tensor, mask, loss_target: torch.Tensor, relative: bool = False):
+    """Drop-in for MaskedAutoencoderViT.forward_learning_loss
+    (/root/reference/Point-MAE_SA3D/models_mae_learn_loss_Classifier_SVM_feature_besed.py:1111-1135; called at
+    engine_pretrain_Classifier_SVM.py:205-215 with the (N, M) per-patch Chamfer matrix as `loss_target`).
+    `mask` is accepted and ignored, as in the reference.  loss_pred (N, L) or (N, L, 1)."""
+    if loss_pred.dim() == 3 and loss_pred.shape[-1] == 1:
+        loss_pred = loss_pred.squeeze(-1)
+    return _LearningLoss.apply(loss_pred.float().contiguous(), loss_target.detach().float().contiguous(), bool(relative))

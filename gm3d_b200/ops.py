@@ -13,7 +13,8 @@ from . import _lib
 
 __all__ = [
     "furthest_point_sample", "fps_centers", "gather", "gather_grad", "knn", "group", "chamfer_forward",
-    "chamfer_fused", "chamfer_backward", "select_patches", "hard_mask", "loss_stats",
+    "chamfer_fused", "chamfer_backward", "select_patches", "hard_mask", "loss_stats", "learning_loss",
+    "scale_translate_", "gather_points",
 ]
 
 
@@ -318,3 +319,56 @@ def loss_stats(per_patch: torch.Tensor) -> torch.Tensor:
         rc = _lib.load().gm3d_loss_stats_f32(_p(per_patch), per_patch.numel(), _p(stats), _stream(per_patch))
     _lib.check("gm3d_loss_stats_f32", rc)
     return stats
+
+
+# ------------------------------------------------------------------ either side of the hot path
+def learning_loss(loss_pred: torch.Tensor, loss_target: torch.Tensor, relative: bool, gscale: float = 1.0,
+                  want_grad: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """forward_learning_loss value (0-d) and gscale * d loss / d loss_pred in one launch
+    (..._feature_besed.py:1111-1135)."""
+    _req(loss_pred, "loss_pred", torch.float32, 2)
+    _req(loss_target, "loss_target", torch.float32, 2)
+    if loss_pred.shape != loss_target.shape:
+        raise ValueError(f"loss_pred {tuple(loss_pred.shape)} and loss_target {tuple(loss_target.shape)} differ")
+    B, L = loss_pred.shape
+    with torch.cuda.device(loss_pred.device):
+        lib = _lib.load()
+        loss = torch.empty((), dtype=torch.float32, device=loss_pred.device)
+        grad = torch.empty_like(loss_pred) if want_grad else None
+        ws = torch.zeros(lib.gm3d_workspace_bytes(_lib.OP_LEARNING_LOSS, B, 0, 0, 0), dtype=torch.uint8, device=loss_pred.device)
+        _lib.check("gm3d_learning_loss_f32", lib.gm3d_learning_loss_f32(
+            _p(loss_pred), _p(loss_target), B, L, int(bool(relative)), float(gscale), _p(loss), _p(grad), _p(ws), _stream(loss_pred)))
+    return loss, grad
+
+
+def scale_translate_(pc: torch.Tensor, scale_shift: torch.Tensor) -> torch.Tensor:
+    """In place pc[b,:,0:3] = pc * scale[b] + shift[b]; scale_shift (B,6) f32 on the same device
+    (datasets/data_transforms.py:20-35 in one launch)."""
+    _req(pc, "pc", torch.float32, 3)
+    _req(scale_shift, "scale_shift", torch.float32, 2)
+    B, N, C = pc.shape
+    if scale_shift.shape != (B, 6):
+        raise ValueError(f"scale_shift must be ({B}, 6), got {tuple(scale_shift.shape)}")
+    with torch.cuda.device(pc.device):
+        _lib.check("gm3d_scale_translate_f32", _lib.load().gm3d_scale_translate_f32(_p(pc), _p(scale_shift), B, N, C, _stream(pc)))
+    return pc
+
+
+def gather_points(xyz: torch.Tensor, idx: torch.Tensor, choice: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[b,j,:] = xyz[b, idx[b, choice[j]], :] -- `fps_idx[:, choice]` + gather_operation + both transposes of
+    engine_finetune.py:132-134 as one gather.  xyz (B,N,3) f32, idx (B,G) int32, choice (K) int64 or None."""
+    _req(xyz, "xyz", torch.float32, 3)
+    _req(idx, "idx", torch.int32, 2)
+    B, N, D = xyz.shape
+    if D != 3 or idx.shape[0] != B:
+        raise ValueError(f"xyz must be (B,N,3) and idx (B,G), got {tuple(xyz.shape)}, {tuple(idx.shape)}")
+    G = idx.shape[1]
+    if choice is not None:
+        _req(choice, "choice", torch.int64, 1)
+        if int(choice.numel()) and (int(choice.min()) < 0 or int(choice.max()) >= G):
+            raise ValueError("choice holds a column outside [0, G)")
+    K = int(choice.numel()) if choice is not None else G
+    with torch.cuda.device(xyz.device):
+        out = torch.empty((B, K, 3), dtype=torch.float32, device=xyz.device)
+        _lib.check("gm3d_gather_points_f32", _lib.load().gm3d_gather_points_f32(_p(xyz), _p(idx), _p(choice), B, N, G, K, _p(out), _stream(xyz)))
+    return out

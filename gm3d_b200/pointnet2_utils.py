@@ -51,3 +51,22 @@ def fps(data: torch.Tensor, number: int) -> torch.Tensor:
     One launch: the FPS kernel writes the gathered centres itself (no transposes, no gather kernel)."""
     _, centers = ops.fps_centers(data, number, want_centers=True)
     return centers
+
+
+def fps_subsample(points: torch.Tensor, npoints: int, point_all: int = None, choice=None) -> torch.Tensor:
+    """The fine-tune / vote-test sub-sampling block (engine_finetune.py:118-134, tools/runner_finetune.py:127-143):
+    FPS down to `point_all` points (1200 / 2400 / 4800 / 8192 for npoints 1024 / 2048 / 4096 / 8192, capped at N),
+    a random `npoints`-column subset of the FPS order (`np.random.choice(point_all, npoints, False)`, drawn here
+    with the same call unless `choice` is given), gather -> (B, npoints, 3).  Two launches, no transposes."""
+    import numpy as np
+    table = {1024: 1200, 2048: 2400, 4096: 4800, 8192: 8192}
+    if point_all is None:
+        if npoints not in table:
+            raise NotImplementedError()
+        point_all = table[npoints]
+    point_all = min(int(point_all), points.size(1))
+    fps_idx = ops.furthest_point_sample(points, point_all)
+    if choice is None:
+        choice = np.random.choice(point_all, npoints, False)
+    choice = torch.as_tensor(np.asarray(choice), dtype=torch.int64).to(points.device)
+    return ops.gather_points(points, fps_idx, choice)

@@ -24,6 +24,12 @@
  *                                                                   models/Point_MAE.py:297-320
  *   gm3d_loss_stats_f32     the scalars fed to misc.all_reduce_mean util/misc.py:345-353,
  *                                                                   engine_pretrain_Classifier_SVM.py:297-305
+ *   gm3d_learning_loss_f32  forward_learning_loss (+ its gradient)   ..._feature_besed.py:1111-1135,
+ *                                                                   engine_pretrain_Classifier_SVM.py:205-215
+ *   gm3d_scale_translate_f32 PointcloudScaleAndTranslate             datasets/data_transforms.py:20-35,
+ *                                                                   engine_pretrain_Classifier_SVM.py:99-100
+ *   gm3d_gather_points_f32  `fps_idx[:, choice]` + gather_operation + transposes of the fine-tune / vote
+ *                           sub-sampling                            engine_finetune.py:132-134, tools/runner_finetune.py:141-143
  *   gm3d_cloud_step_f32     one pre-training step of the path in one launch: Group.forward ->
  *                           generate_mask -> forward_loss -> backward   engine_pretrain_Classifier_SVM.py:108-118,157-184
  *
@@ -51,7 +57,7 @@
 extern "C" {
 #endif
 
-#define GM3D_ABI_VERSION 2
+#define GM3D_ABI_VERSION 3
 
 #define GM3D_OK 0
 #define GM3D_EINVAL (-1)  /* bad shape: B/N/G/k <= 0, k > N, G > N, NULL required pointer ...        */
@@ -66,6 +72,7 @@ extern "C" {
 #define GM3D_OP_HARD_MASK 6
 #define GM3D_OP_LOSS_STATS 7
 #define GM3D_OP_CLOUD_STEP 8
+#define GM3D_OP_LEARNING_LOSS 9
 
 /* Largest k gm3d_knn_f32 / gm3d_group_f32 accept (one warp holds the sorted k-list, one entry per lane). */
 #define GM3D_KNN_MAX_K 32
@@ -192,6 +199,28 @@ int gm3d_cloud_step_f32(const float* xyz, int B, int N, int G, int k, int32_t* f
                         float gscale1, float gscale2, int norm /* 1|2 */, float* dist1, float* dist2, int32_t* idx1,
                         int32_t* idx2, float* per_patch, float* total, float* stats, float* gxyz1 /* (B*M,k,3) */,
                         int flags /* GM3D_STEP_* or 0 */, void* ws, void* stream);
+
+/* ---- the operators either side of the hot path ------------------------------------------------ */
+
+/* forward_learning_loss.  loss_pred, loss_target (B, L) f32 -> loss (1) and, when grad != NULL,
+ * grad (B, L) = gscale * d loss / d loss_pred (gscale = the upstream gradient of the scalar).
+ *   relative != 0: pairwise ranking BCE, sum_{i,j} [t_j > t_i] -log(sigmoid(p_j - p_i) + 1e-6)
+ *                  + [t_j < t_i] -log(1 - sigmoid(p_j - p_i) + 1e-6), divided by the number of ordered pairs with
+ *                  t_i != t_j in the whole batch;
+ *   relative == 0: mean((p - (t - mean_row) / sqrt(var_row + 1e-6))^2), var unbiased.
+ * ws: gm3d_workspace_bytes(GM3D_OP_LEARNING_LOSS, B, 0, 0, 0) bytes, first 16 zero before the first launch.
+ * Deterministic (fixed summation order, ticket for the batch totals).  L <= 4096. */
+int gm3d_learning_loss_f32(const float* loss_pred, const float* loss_target, int B, int L, int relative, float gscale,
+                           float* loss, float* grad /* or NULL */, void* ws, void* stream);
+
+/* In place pc[b, n, 0:3] = pc[b, n, 0:3] * scale[b] + shift[b] (multiply and add rounded separately, as
+ * torch.mul followed by +).  pc (B, N, C >= 3) f32; scale_shift (B, 6) f32 = scale xyz, shift xyz. */
+int gm3d_scale_translate_f32(float* pc, const float* scale_shift, int B, int N, int C, void* stream);
+
+/* out[b, j, :] = xyz[b, idx[b, choice ? choice[j] : j], :].  xyz (B, N, 3) f32, idx (B, G) int32,
+ * choice (K) int64 column subset or NULL (then K <= G), out (B, K, 3). */
+int gm3d_gather_points_f32(const float* xyz, const int32_t* idx, const int64_t* choice /* or NULL */, int B, int N,
+                           int G, int K, float* out, void* stream);
 
 #ifdef __cplusplus
 }

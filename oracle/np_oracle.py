@@ -255,3 +255,42 @@ def rand_mask(rand_keys, num_mask: int) -> np.ndarray:
     rand_keys = np.asarray(rand_keys, dtype=F32)
     B, G = rand_keys.shape
     return hard_mask(np.zeros((B, G), dtype=F32), G - num_mask, 0, rand_keys)
+
+
+# ------------------------------------------------------------------ SURVEY 8(f) rows
+def learning_loss(loss_pred, loss_target, relative):
+    """forward_learning_loss and its gradient w.r.t. loss_pred, float64
+    (/root/reference/Point-MAE_SA3D/models_mae_learn_loss_Classifier_SVM_feature_besed.py:1111-1135)."""
+    p = np.asarray(loss_pred, dtype=np.float64)
+    t = np.asarray(loss_target, dtype=np.float64)
+    if relative:
+        pos = t[:, None, :] > t[:, :, None]          # [n, i, j]: t_j > t_i
+        neg = t[:, None, :] < t[:, :, None]
+        m = p[:, None, :] - p[:, :, None]            # p_j - p_i
+        s = 1.0 / (1.0 + np.exp(-m))
+        valid = float(pos.sum() + neg.sum())
+        loss = (-(pos * np.log(s + 1e-6)) - (neg * np.log(1 - s + 1e-6))).sum() / valid
+        dm = (-(pos * s * (1 - s) / (s + 1e-6)) + (neg * s * (1 - s) / (1 - s + 1e-6))) / valid  # d loss / d m[n,i,j]
+        grad = dm.sum(axis=1) - dm.sum(axis=2)       # + as second index j, - as first index i
+        return loss, grad
+    mean = t.mean(axis=1, keepdims=True)
+    var = t.var(axis=1, keepdims=True, ddof=1)
+    tn = (t - mean) / np.sqrt(var + 1e-6)
+    d = p - tn
+    return (d ** 2).mean(), 2.0 * d / d.size
+
+
+def scale_translate(pc, scale_shift):
+    """PointcloudScaleAndTranslate arithmetic (datasets/data_transforms.py:33): fp32 multiply, then fp32 add."""
+    pc = np.array(pc, dtype=np.float32, copy=True)
+    ss = np.asarray(scale_shift, dtype=np.float32)
+    pc[:, :, 0:3] = (pc[:, :, 0:3] * ss[:, None, 0:3]).astype(np.float32) + ss[:, None, 3:6]
+    return pc
+
+
+def gather_points(xyz, idx, choice=None):
+    """xyz (B,N,3), idx (B,G) -> xyz[b, idx[b, choice]] (engine_finetune.py:132-134 without the transposes)."""
+    xyz, idx = np.asarray(xyz), np.asarray(idx)
+    if choice is not None:
+        idx = idx[:, np.asarray(choice)]
+    return np.take_along_axis(xyz, idx[:, :, None].astype(np.int64), axis=1)

@@ -573,3 +573,77 @@ def test_step_ring_overlapped_steps_equal_serial_steps(cuda):
     for s, w in zip(steps, want):
         for n, v in w.items():
             assert np.array_equal(host(getattr(s, n)), v), n
+
+
+# ------------------------------------------------------------------------------------------ SURVEY 8(f) rows
+@pytest.fixture(scope="module")
+def golden_next():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_next.npz"))
+
+
+@pytest.mark.parametrize("tag", ["c2", "small", "m2ae"])
+@pytest.mark.parametrize("rel", [True, False])
+def test_learning_loss_matches_reference_golden_and_oracle(cuda, golden_next, tag, rel):
+    """forward_learning_loss value and autograd gradient against the reference's own function (golden) and the
+    float64 oracle; tolerance 1e-5 relative on the loss, 1e-4 of the largest gradient entry (fp32 exp/log)."""
+    from gm3d_b200.loss import forward_learning_loss
+    p = dev(golden_next[f"ll_{tag}_pred"], cuda).requires_grad_(True)
+    t = dev(golden_next[f"ll_{tag}_target"], cuda)
+    loss = forward_learning_loss(p.unsqueeze(-1) if tag == "small" else p, None, t, relative=rel)
+    (3.0 * loss).backward()
+    want = float(golden_next[f"ll_{tag}_rel{int(rel)}_loss"])
+    assert abs(loss.item() - want) <= 1e-5 * abs(want)
+    wg = 3.0 * golden_next[f"ll_{tag}_rel{int(rel)}_grad"]
+    assert np.abs(host(p.grad) - wg).max() <= 1e-4 * np.abs(wg).max()
+    ol, og = no.learning_loss(golden_next[f"ll_{tag}_pred"], golden_next[f"ll_{tag}_target"], rel)
+    assert abs(loss.item() - ol) <= 1e-5 * abs(ol)
+    assert np.abs(host(p.grad) - 3.0 * og).max() <= 1e-4 * np.abs(og).max() * 3.0
+
+
+def test_learning_loss_full_size_and_determinism(cuda):
+    from gm3d_b200 import ops
+    rng = np.random.default_rng(3)
+    p = rng.standard_normal((128, 39)).astype(np.float32)
+    t = (rng.random((128, 39)) * 0.05).astype(np.float32)
+    a = ops.learning_loss(dev(p, cuda), dev(t, cuda), True)
+    b = ops.learning_loss(dev(p, cuda), dev(t, cuda), True)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])  # fixed summation order
+    ol, og = no.learning_loss(p, t, True)
+    assert abs(a[0].item() - ol) <= 1e-5 * abs(ol)
+    assert np.abs(host(a[1]) - og).max() <= 1e-4 * np.abs(og).max()
+    # antisymmetry of the pairwise logits: a constant shift of the predictions changes nothing
+    c = ops.learning_loss(dev(p + 0.5, cuda), dev(t, cuda), True)
+    assert abs(c[0].item() - a[0].item()) <= 1e-5 * abs(a[0].item())
+    assert abs(host(a[1]).sum()) <= 1e-4 * np.abs(host(a[1])).sum()
+
+
+def test_scale_and_translate_dropin(cuda, golden_next):
+    """Seeded like the reference run that produced the golden: same NumPy stream, bit-identical clouds."""
+    from gm3d_b200.transforms import PointcloudScaleAndTranslate
+    pc = dev(golden_next["sat_in"], cuda)
+    np.random.seed(2003)
+    out = PointcloudScaleAndTranslate()(pc)
+    assert out.data_ptr() == pc.data_ptr()  # in place, like the reference
+    assert np.array_equal(host(out), golden_next["sat_out"])
+    # extra channels (normals) stay untouched
+    from gm3d_b200 import ops
+    x6 = np.random.default_rng(1).standard_normal((3, 50, 6)).astype(np.float32)
+    ss = np.random.default_rng(2).uniform(0.5, 1.5, (3, 6)).astype(np.float32)
+    got = host(ops.scale_translate_(dev(x6, cuda), dev(ss, cuda)))
+    assert np.array_equal(got[:, :, :3], no.scale_translate(x6[:, :, :3], ss)) and np.array_equal(got[:, :, 3:], x6[:, :, 3:])
+
+
+def test_fps_subsample_matches_reference_golden(cuda, golden_next):
+    from gm3d_b200.pointnet2_utils import fps_subsample
+    pts = dev(golden_next["ft_points"], cuda)
+    got = fps_subsample(pts, 1024, choice=golden_next["ft_choice"])
+    assert np.array_equal(host(got), golden_next["ft_out"])
+    np.random.seed(2007)  # the same draw the reference made
+    assert np.array_equal(host(fps_subsample(pts, 1024)), golden_next["ft_out"])
+    # G == N edge (engine_finetune.py:129-130): point_all capped at N
+    small = dev(synthetic_clouds(2, 600, 9), cuda)
+    np.random.seed(1)
+    ch = np.random.choice(600, 512, False)
+    assert np.array_equal(host(fps_subsample(small, 512, point_all=1200, choice=ch)),
+                          no.gather_points(host(small), co.fps(host(small), 600), ch))

@@ -235,3 +235,30 @@ def test_gather_and_grad():
     assert np.array_equal(co.gather(f, idx), no.gather(f, idx))
     go = rng.standard_normal((2, 3, 20)).astype(np.float32)
     assert np.array_equal(co.gather_grad(go, idx, 50), no.gather_grad(go, idx, 50))
+
+
+# ------------------------------------------------------------------ SURVEY 8(f) rows vs the reference's own functions
+@pytest.fixture(scope="module")
+def golden_next():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_next.npz"))
+
+
+@pytest.mark.parametrize("tag", ["c2", "small", "m2ae"])
+@pytest.mark.parametrize("rel", [1, 0])
+def test_learning_loss_oracle_matches_reference(golden_next, tag, rel):
+    from oracle import np_oracle as no
+    loss, grad = no.learning_loss(golden_next[f"ll_{tag}_pred"], golden_next[f"ll_{tag}_target"], bool(rel))
+    assert abs(loss - float(golden_next[f"ll_{tag}_rel{rel}_loss"])) <= 2e-6 * abs(loss)
+    want = golden_next[f"ll_{tag}_rel{rel}_grad"]
+    assert np.abs(grad - want).max() <= 2e-5 * np.abs(want).max()
+
+
+def test_scale_translate_and_subsample_oracle_match_reference(golden_next):
+    from oracle import c_oracle as co
+    from oracle import np_oracle as no
+    out = no.scale_translate(golden_next["sat_in"], golden_next["sat_draws"].astype(np.float32))
+    assert np.array_equal(out, golden_next["sat_out"])
+    pts, choice = golden_next["ft_points"], golden_next["ft_choice"]
+    idx = co.fps(pts, int(golden_next["ft_point_all"][0]))
+    assert np.array_equal(no.gather_points(pts, idx, choice), golden_next["ft_out"])
