@@ -28,8 +28,8 @@ __device__ __forceinline__ void bce_terms(float m, float& lp, float& ln, float& 
 // One CTA per row.  relative: loss_n = sum_{i,j} [t_j > t_i] lp(p_j - p_i) + [t_j < t_i] ln(p_j - p_i), valid_n = #pairs with
 // t_i != t_j; the batch loss is sum_n loss_n / sum_n valid_n, so the gradient written here is UN-normalised and the
 // last CTA (ticket) reduces the per-row partials in row order, writes the loss and scales the whole gradient.
-// Thread i owns element i of the row: as first index of the pair (i, j) the logit falls with p_i, as second index of
-// (j, i) it rises -- both sums run over j in ascending order (deterministic).
+// A warp owns element i of the row and its lanes stride over j: as first index of the pair (i, j) the logit falls
+// with p_i, as second index of (j, i) it rises; lane partials are combined by a fixed butterfly (deterministic).
 __global__ void __launch_bounds__(kLlThreads)
     learning_loss_relative_kernel(const float* __restrict__ pred, const float* __restrict__ target, int B, int L,
                                   float* __restrict__ loss, float* __restrict__ grad, double* __restrict__ partial,
@@ -46,10 +46,11 @@ __global__ void __launch_bounds__(kLlThreads)
     }
     __syncthreads();
     double sum = 0.0, cnt = 0.0;
-    for (int i = tid; i < L; i += kLlThreads) {
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int i = warp; i < L; i += kLlThreads / 32) {  // one warp per element i, lanes stride over j
         const float pi = sp[i], ti = st[i];
         float g = 0.0f;
-        for (int j = 0; j < L; ++j) {
+        for (int j = lane; j < L; j += 32) {
             const float pj = sp[j], tj = st[j];
             if (tj == ti) continue;  // neither positive nor negative (includes j == i)
             float lp, ln, dlp, dln;
@@ -60,7 +61,9 @@ __global__ void __launch_bounds__(kLlThreads)
             bce_terms(pi - pj, lp, ln, dlp, dln);       // pair (j, i): logit p_i - p_j, labels swap
             g += ti > tj ? dlp : dln;                    // d/dp_i of pair (j, i)
         }
-        if (grad) grad[static_cast<size_t>(b) * L + i] = g;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(kFull, g, o);  // fixed butterfly order
+        if (grad && lane == 0) grad[static_cast<size_t>(b) * L + i] = g;
     }
     __threadfence();  // the last CTA rescales every row's gradient
 #pragma unroll
@@ -83,11 +86,15 @@ __global__ void __launch_bounds__(kLlThreads)
     __threadfence();
     // last CTA: batch totals in row order, the loss, and the gradient scale
     __shared__ double s_tot[2];
-    if (tid == 0) {
+    if (tid < 32) {  // lanes take rows r = lane, lane + 32, ... then a fixed butterfly: deterministic
         double ts = 0.0, tc = 0.0;
-        for (int r = 0; r < B; ++r) ts += __ldcg(partial + 2 * r), tc += __ldcg(partial + 2 * r + 1);
-        s_tot[0] = ts, s_tot[1] = tc;
-        loss[0] = static_cast<float>(ts / tc);
+        for (int r = tid; r < B; r += 32) ts += __ldcg(partial + 2 * r), tc += __ldcg(partial + 2 * r + 1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ts += __shfl_xor_sync(kFull, ts, o), tc += __shfl_xor_sync(kFull, tc, o);
+        if (tid == 0) {
+            s_tot[0] = ts, s_tot[1] = tc;
+            loss[0] = static_cast<float>(ts / tc);
+        }
     }
     __syncthreads();
     if (grad) {
@@ -150,23 +157,39 @@ __global__ void __launch_bounds__(kLlThreads)
         if (s_last) *ticket = 0u;
     }
     __syncthreads();
-    if (s_last && tid == 0) {
+    if (s_last && tid < 32) {
         __threadfence();
         double ts = 0.0, tc = 0.0;
-        for (int r = 0; r < B; ++r) ts += __ldcg(partial + 2 * r), tc += __ldcg(partial + 2 * r + 1);
-        loss[0] = static_cast<float>(ts / tc);
+        for (int r = tid; r < B; r += 32) ts += __ldcg(partial + 2 * r), tc += __ldcg(partial + 2 * r + 1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ts += __shfl_xor_sync(kFull, ts, o), tc += __shfl_xor_sync(kFull, tc, o);
+        if (tid == 0) loss[0] = static_cast<float>(ts / tc);
     }
     (void)s_stat;
 }
 
 // pc[b, n, 0:3] = pc * scale[b] + shift[b]: multiply and add rounded separately, like torch.mul followed by `+`.
+// C == 3 and N % 4 == 0 (16-byte aligned rows): a thread moves 4 points = three LDG.128 / STG.128, whose lanes see the
+// coordinate pattern xyzx yzxy zxyz.
 __global__ void __launch_bounds__(256)
-    scale_translate_kernel(float* __restrict__ pc, const float* __restrict__ ss, int N, int C) {
+    scale_translate_kernel(float* __restrict__ pc, const float* __restrict__ ss, int N, int C, int vec) {
     const int b = blockIdx.y;
     const float sx = ss[b * 6 + 0], sy = ss[b * 6 + 1], sz = ss[b * 6 + 2];
     const float tx = ss[b * 6 + 3], ty = ss[b * 6 + 4], tz = ss[b * 6 + 5];
     float* row = pc + static_cast<size_t>(b) * N * C;
-    if (C == 3) {  // flat, coalesced: element e is coordinate e % 3
+    if (vec) {
+        float4* r4 = reinterpret_cast<float4*>(row);
+        for (int q = blockIdx.x * 256 + threadIdx.x; q < N / 4; q += gridDim.x * 256) {
+            float4 a = r4[3 * q], c = r4[3 * q + 1], d = r4[3 * q + 2];
+            a.x = __fadd_rn(__fmul_rn(a.x, sx), tx), a.y = __fadd_rn(__fmul_rn(a.y, sy), ty);
+            a.z = __fadd_rn(__fmul_rn(a.z, sz), tz), a.w = __fadd_rn(__fmul_rn(a.w, sx), tx);
+            c.x = __fadd_rn(__fmul_rn(c.x, sy), ty), c.y = __fadd_rn(__fmul_rn(c.y, sz), tz);
+            c.z = __fadd_rn(__fmul_rn(c.z, sx), tx), c.w = __fadd_rn(__fmul_rn(c.w, sy), ty);
+            d.x = __fadd_rn(__fmul_rn(d.x, sz), tz), d.y = __fadd_rn(__fmul_rn(d.y, sx), tx);
+            d.z = __fadd_rn(__fmul_rn(d.z, sy), ty), d.w = __fadd_rn(__fmul_rn(d.w, sz), tz);
+            r4[3 * q] = a, r4[3 * q + 1] = c, r4[3 * q + 2] = d;
+        }
+    } else if (C == 3) {  // flat: element e is coordinate e % 3
         for (int e = blockIdx.x * 256 + threadIdx.x; e < 3 * N; e += gridDim.x * 256) {
             const int c = e % 3;
             const float s = c == 0 ? sx : (c == 1 ? sy : sz), t = c == 0 ? tx : (c == 1 ? ty : tz);
@@ -221,10 +244,11 @@ GM3D_API int gm3d_scale_translate_f32(float* pc, const float* scale_shift, int B
     using namespace gm3d;
     if (!pc || !scale_shift || B <= 0 || N <= 0 || C < 3) return GM3D_EINVAL;
     if (B > 65535) return GM3D_ENOSUP;
-    const int work = C == 3 ? 3 * N : N;
+    const int vec = C == 3 && N % 4 == 0 && reinterpret_cast<uintptr_t>(pc) % 16 == 0;
+    const int work = vec ? N / 4 : (C == 3 ? 3 * N : N);
     int gx = (work + 255) / 256;
     if (gx > 64) gx = 64;
-    scale_translate_kernel<<<dim3(gx, B), 256, 0, as_stream(stream)>>>(pc, scale_shift, N, C);
+    scale_translate_kernel<<<dim3(gx, B), 256, 0, as_stream(stream)>>>(pc, scale_shift, N, C, vec);
     return launch_status();
 }
 

@@ -322,6 +322,9 @@ def loss_stats(per_patch: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------ either side of the hot path
+_LL_WS = {}
+
+
 def learning_loss(loss_pred: torch.Tensor, loss_target: torch.Tensor, relative: bool, gscale: float = 1.0,
                   want_grad: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """forward_learning_loss value (0-d) and gscale * d loss / d loss_pred in one launch
@@ -335,7 +338,11 @@ def learning_loss(loss_pred: torch.Tensor, loss_target: torch.Tensor, relative: 
         lib = _lib.load()
         loss = torch.empty((), dtype=torch.float32, device=loss_pred.device)
         grad = torch.empty_like(loss_pred) if want_grad else None
-        ws = torch.zeros(lib.gm3d_workspace_bytes(_lib.OP_LEARNING_LOSS, B, 0, 0, 0), dtype=torch.uint8, device=loss_pred.device)
+        need = lib.gm3d_workspace_bytes(_lib.OP_LEARNING_LOSS, B, 0, 0, 0)
+        key = (loss_pred.device.index, torch.cuda.current_stream(loss_pred.device).cuda_stream)
+        ws = _LL_WS.get(key)
+        if ws is None or ws.numel() < need:  # one workspace per (device, stream): the ticket resets itself
+            ws = _LL_WS[key] = torch.zeros(max(need, 4096), dtype=torch.uint8, device=loss_pred.device)
         _lib.check("gm3d_learning_loss_f32", lib.gm3d_learning_loss_f32(
             _p(loss_pred), _p(loss_target), B, L, int(bool(relative)), float(gscale), _p(loss), _p(grad), _p(ws), _stream(loss_pred)))
     return loss, grad
@@ -354,7 +361,8 @@ def scale_translate_(pc: torch.Tensor, scale_shift: torch.Tensor) -> torch.Tenso
     return pc
 
 
-def gather_points(xyz: torch.Tensor, idx: torch.Tensor, choice: Optional[torch.Tensor] = None) -> torch.Tensor:
+def gather_points(xyz: torch.Tensor, idx: torch.Tensor, choice: Optional[torch.Tensor] = None,
+                  validate: bool = True) -> torch.Tensor:
     """out[b,j,:] = xyz[b, idx[b, choice[j]], :] -- `fps_idx[:, choice]` + gather_operation + both transposes of
     engine_finetune.py:132-134 as one gather.  xyz (B,N,3) f32, idx (B,G) int32, choice (K) int64 or None."""
     _req(xyz, "xyz", torch.float32, 3)
@@ -365,7 +373,8 @@ def gather_points(xyz: torch.Tensor, idx: torch.Tensor, choice: Optional[torch.T
     G = idx.shape[1]
     if choice is not None:
         _req(choice, "choice", torch.int64, 1)
-        if int(choice.numel()) and (int(choice.min()) < 0 or int(choice.max()) >= G):
+        # (range check reads the tensor back: pass validate=False inside a CUDA-graph capture)
+        if validate and int(choice.numel()) and (int(choice.min()) < 0 or int(choice.max()) >= G):
             raise ValueError("choice holds a column outside [0, G)")
     K = int(choice.numel()) if choice is not None else G
     with torch.cuda.device(xyz.device):
