@@ -11,7 +11,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_PKG, "libgm3d_sm100.so")
 
-GM3D_ABI_VERSION = 3
+GM3D_ABI_VERSION = 4
 GM3D_EINVAL, GM3D_ENOSUP, GM3D_EALIGN = -1, -2, -3
 OP_FPS, OP_KNN, OP_GROUP, OP_CHAMFER_FWD, OP_CHAMFER_BWD, OP_HARD_MASK, OP_LOSS_STATS, OP_CLOUD_STEP, OP_LEARNING_LOSS = range(1, 10)
 KNN_MAX_K = 32
@@ -40,6 +40,7 @@ SIGNATURES = {
     "gm3d_learning_loss_f32": (_i, [_vp, _vp, _i, _i, _i, ctypes.c_float, _vp, _vp, _vp, _vp]),
     "gm3d_scale_translate_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "gm3d_gather_points_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "gm3d_encoder_fwd_bf16": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "gm3d_cloud_step_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _u64, _u64, _vp, _vp, _vp,
                                  ctypes.c_float, ctypes.c_float, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
 }

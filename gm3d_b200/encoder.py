@@ -1,0 +1,67 @@
+"""Patch Encoder (mini-PointNet) on the B200 tensor cores -- inference form of the reference module
+(/root/reference/Point-MAE_SA3D/models/Point_MAE.py:16-47): Conv1d(3,128)-BN-ReLU-Conv1d(128,256), max over the
+patch, concat, Conv1d(512,512)-BN-ReLU-Conv1d(512,C), max over the patch.
+
+`EncoderB200.from_state_dict(encoder.state_dict())` folds the two BatchNorm layers (running statistics) into
+the adjacent convolutions, reorders the concat so the per-point half of W3 comes first, casts the three GEMM
+weights to BF16 once, and `forward` is ONE launch of gm3d_encoder_fwd_bf16 (tcgen05 + TMEM, activations never
+leave the SM).  Training-mode BatchNorm (batch statistics) and the backward are not served by this kernel.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def _fold(w: torch.Tensor, b: torch.Tensor, bn_w, bn_b, mean, var, eps: float):
+    s = bn_w / torch.sqrt(var + eps)
+    return w * s[:, None], (b - mean) * s + bn_b
+
+
+class EncoderB200(torch.nn.Module):
+    def __init__(self, encoder_channel: int, w1, b1, w2, b2, w3, b3, w4, b4):
+        super().__init__()
+        self.encoder_channel = encoder_channel
+        f32, bf16 = torch.float32, torch.bfloat16
+        self.register_buffer("w1", w1.to(f32).contiguous())
+        self.register_buffer("b1", b1.to(f32).contiguous())
+        self.register_buffer("w2", w2.to(bf16).contiguous())
+        self.register_buffer("b2", b2.to(f32).contiguous())
+        self.register_buffer("w3", w3.to(bf16).contiguous())
+        self.register_buffer("b3", b3.to(f32).contiguous())
+        self.register_buffer("w4", w4.to(bf16).contiguous())
+        self.register_buffer("b4", b4.to(f32).contiguous())
+
+    @classmethod
+    def from_state_dict(cls, sd, eps: float = 1e-5) -> "EncoderB200":
+        """sd: state_dict of the reference Encoder (first_conv.{0,1,3}.*, second_conv.{0,1,3}.*)."""
+        g = lambda k: sd[k].detach().float()  # noqa: E731
+        w1, b1 = _fold(g("first_conv.0.weight")[:, :, 0], g("first_conv.0.bias"), g("first_conv.1.weight"),
+                       g("first_conv.1.bias"), g("first_conv.1.running_mean"), g("first_conv.1.running_var"), eps)
+        w2, b2 = g("first_conv.3.weight")[:, :, 0], g("first_conv.3.bias")
+        w3, b3 = _fold(g("second_conv.0.weight")[:, :, 0], g("second_conv.0.bias"), g("second_conv.1.weight"),
+                       g("second_conv.1.bias"), g("second_conv.1.running_mean"), g("second_conv.1.running_var"), eps)
+        # reference concat is [global (256) ; per-point (256)]; the kernel's A operand is [per-point ; global]
+        w3 = torch.cat([w3[:, 256:], w3[:, :256]], dim=1)
+        w4, b4 = g("second_conv.3.weight")[:, :, 0], g("second_conv.3.bias")
+        return cls(w4.shape[0], w1, b1, w2, b2, w3, b3, w4, b4)
+
+    def forward(self, point_groups: torch.Tensor) -> torch.Tensor:
+        """point_groups (B, G, 32, 3) f32 CUDA -> (B, G, C) f32."""
+        if not point_groups.is_cuda:
+            raise RuntimeError("EncoderB200 runs on CUDA only (gm3d_b200 has no CPU fallback)")
+        bs, g, n, d = point_groups.shape
+        if d != 3:
+            raise ValueError("point_groups must be (B, G, n, 3)")
+        x = point_groups.float().contiguous()
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            out = torch.empty((bs, g, self.encoder_channel), dtype=torch.float32, device=x.device)
+            status = torch.zeros((1,), dtype=torch.int32, device=x.device)
+            _lib.check("gm3d_encoder_fwd_bf16", lib.gm3d_encoder_fwd_bf16(
+                x.data_ptr(), bs * g, n, self.w1.data_ptr(), self.b1.data_ptr(), self.w2.data_ptr(), self.b2.data_ptr(),
+                self.w3.data_ptr(), self.b3.data_ptr(), self.w4.data_ptr(), self.b4.data_ptr(), self.encoder_channel,
+                out.data_ptr(), status.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream))
+        self.last_status = status
+        return out

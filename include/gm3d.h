@@ -30,6 +30,7 @@
  *                                                                   engine_pretrain_Classifier_SVM.py:99-100
  *   gm3d_gather_points_f32  `fps_idx[:, choice]` + gather_operation + transposes of the fine-tune / vote
  *                           sub-sampling                            engine_finetune.py:132-134, tools/runner_finetune.py:141-143
+ *   gm3d_encoder_fwd_bf16   Encoder.forward (mini-PointNet, eval)   models/Point_MAE.py:16-47,562
  *   gm3d_cloud_step_f32     one pre-training step of the path in one launch: Group.forward ->
  *                           generate_mask -> forward_loss -> backward   engine_pretrain_Classifier_SVM.py:108-118,157-184
  *
@@ -57,7 +58,7 @@
 extern "C" {
 #endif
 
-#define GM3D_ABI_VERSION 3
+#define GM3D_ABI_VERSION 4
 
 #define GM3D_OK 0
 #define GM3D_EINVAL (-1)  /* bad shape: B/N/G/k <= 0, k > N, G > N, NULL required pointer ...        */
@@ -221,6 +222,17 @@ int gm3d_scale_translate_f32(float* pc, const float* scale_shift, int B, int N, 
  * choice (K) int64 column subset or NULL (then K <= G), out (B, K, 3). */
 int gm3d_gather_points_f32(const float* xyz, const int32_t* idx, const int64_t* choice /* or NULL */, int B, int N,
                            int G, int K, float* out, void* stream);
+
+/* Patch Encoder (mini-PointNet) forward in inference form on the tcgen05 tensor cores (BF16 operands, FP32
+ * accumulation; ~1e-2 relative to the FP32 reference, which itself runs under fp16 autocast).
+ * nbhd (P, 32, 3) f32 -> out (P, C) f32, C a multiple of 16, C <= 512 (Point-MAE: 384).  BatchNorm is folded by
+ * the caller: w1 (128,3) f32, b1 (128); w2 (256,128) bf16, b2 (256); w3 (512,512) bf16 with its input columns
+ * ordered [per-point feature (256) ; patch maximum (256)], b3 (512); w4 (C,512) bf16, b4 (C).  bf16 pointers
+ * 16-byte aligned.  *status (device int32 or NULL) is set to 1 if a tensor-core batch never completed.
+ * n_points must be 32 (one warp per patch), else GM3D_ENOSUP. */
+int gm3d_encoder_fwd_bf16(const float* nbhd, int P, int n_points, const float* w1, const float* b1, const void* w2,
+                          const float* b2, const void* w3, const float* b3, const void* w4, const float* b4, int C,
+                          float* out, int32_t* status /* or NULL */, void* stream);
 
 #ifdef __cplusplus
 }

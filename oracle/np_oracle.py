@@ -294,3 +294,26 @@ def gather_points(xyz, idx, choice=None):
     if choice is not None:
         idx = idx[:, np.asarray(choice)]
     return np.take_along_axis(xyz, idx[:, :, None].astype(np.int64), axis=1)
+
+
+def encoder_eval(point_groups, sd, eps=1e-5):
+    """Encoder.forward in eval mode, float64 (/root/reference/Point-MAE_SA3D/models/Point_MAE.py:16-47).
+    point_groups (B,G,n,3); sd: dict of the reference state_dict arrays keyed like `first_conv.0.weight`."""
+    x = np.asarray(point_groups, dtype=np.float64)
+    bs, g, n, _ = x.shape
+    x = x.reshape(bs * g, n, 3)
+
+    def conv(v, w, b):  # v (P, n, cin), w (cout, cin, 1)
+        return v @ np.asarray(w, dtype=np.float64)[:, :, 0].T + np.asarray(b, dtype=np.float64)
+
+    def bn(v, pre):
+        m, var = np.asarray(sd[pre + ".running_mean"], np.float64), np.asarray(sd[pre + ".running_var"], np.float64)
+        return (v - m) / np.sqrt(var + eps) * np.asarray(sd[pre + ".weight"], np.float64) + np.asarray(sd[pre + ".bias"], np.float64)
+
+    h = np.maximum(bn(conv(x, sd["first_conv.0.weight"], sd["first_conv.0.bias"]), "first_conv.1"), 0.0)
+    f = conv(h, sd["first_conv.3.weight"], sd["first_conv.3.bias"])            # (P, n, 256)
+    gmax = f.max(axis=1, keepdims=True)
+    cat = np.concatenate([np.broadcast_to(gmax, f.shape), f], axis=2)           # [global ; per-point]
+    h2 = np.maximum(bn(conv(cat, sd["second_conv.0.weight"], sd["second_conv.0.bias"]), "second_conv.1"), 0.0)
+    out = conv(h2, sd["second_conv.3.weight"], sd["second_conv.3.bias"]).max(axis=1)
+    return out.reshape(bs, g, -1)

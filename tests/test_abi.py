@@ -35,7 +35,7 @@ def test_header_symbols_are_all_exported_and_bound():
 def test_version_errors_and_workspace_are_host_only():
     from gm3d_b200 import _lib
     lib = _lib.load()
-    assert lib.gm3d_abi_version() == _lib.GM3D_ABI_VERSION == 3
+    assert lib.gm3d_abi_version() == _lib.GM3D_ABI_VERSION == 4
     assert b"invalid" in lib.gm3d_strerror(_lib.GM3D_EINVAL)
     assert b"not supported" in lib.gm3d_strerror(_lib.GM3D_ENOSUP)
     assert lib.gm3d_strerror(0) == b"success"

@@ -647,3 +647,43 @@ def test_fps_subsample_matches_reference_golden(cuda, golden_next):
     ch = np.random.choice(600, 512, False)
     assert np.array_equal(host(fps_subsample(small, 512, point_all=1200, choice=ch)),
                           no.gather_points(host(small), co.fps(host(small), 600), ch))
+
+
+def _encoder_sd(golden_next):
+    from test_oracle import _encoder_state_dict
+    return {k: torch.from_numpy(v) for k, v in _encoder_state_dict(golden_next).items()}
+
+
+def test_encoder_tcgen05_matches_reference_golden(cuda, golden_next):
+    """tcgen05 Encoder (BF16 operands, FP32 accumulate) against the reference module's own FP32 output: the
+    tolerance is BF16's -- 1e-2 of the output range at worst, 2e-3 on average."""
+    from gm3d_b200.encoder import EncoderB200
+    enc = EncoderB200.from_state_dict(_encoder_sd(golden_next)).to(cuda)
+    got = host(enc(dev(golden_next["enc_neighborhood"], cuda)))
+    assert enc.last_status.item() == 0
+    want = golden_next["enc_out"]
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= 1e-2 * scale
+    assert np.abs(got - want).mean() <= 2e-3 * scale
+
+
+def test_encoder_tcgen05_full_size_vs_oracle_and_properties(cuda, golden_next):
+    """Pre-training size (B=128, G=64: 8192 patches, 64 tiles per SM-slot), ragged patch count, determinism, and
+    permutation invariance over the points of a patch (both max-pools)."""
+    from gm3d_b200.encoder import EncoderB200
+    sd = _encoder_sd(golden_next)
+    enc = EncoderB200.from_state_dict(sd).to(cuda)
+    rng = np.random.default_rng(12)
+    nb = (rng.standard_normal((128, 64, 32, 3)) * 0.08).astype(np.float32)
+    a = enc(dev(nb, cuda))
+    b = enc(dev(nb, cuda))
+    assert enc.last_status.item() == 0 and torch.equal(a, b)
+    sub = no.encoder_eval(nb[:2], {k: v.numpy() for k, v in sd.items()})
+    assert np.abs(host(a)[:2] - sub).max() <= 1e-2 * np.abs(sub).max()
+    perm = rng.permutation(32)
+    c = enc(dev(nb[:, :, perm], cuda))
+    assert np.abs(host(c) - host(a)).max() <= 1e-2 * np.abs(host(a)).max()   # BF16 rounding differs per row order only
+    odd = enc(dev(nb[:1, :7], cuda))                                          # 7 patches: a partial tile
+    assert np.array_equal(host(odd), host(a)[:1, :7])
+    with pytest.raises(NotImplementedError):
+        enc(dev(nb[:1, :4, :16], cuda))                                       # n != 32

@@ -262,3 +262,23 @@ def test_scale_translate_and_subsample_oracle_match_reference(golden_next):
     pts, choice = golden_next["ft_points"], golden_next["ft_choice"]
     idx = co.fps(pts, int(golden_next["ft_point_all"][0]))
     assert np.array_equal(no.gather_points(pts, idx, choice), golden_next["ft_out"])
+
+
+def _encoder_state_dict(golden_next):
+    sd = {}
+    for k in golden_next.files:
+        if k.startswith("enc_w_"):
+            a, i, name = k[len("enc_w_"):].split("_", 2)[0:3] if not k[len("enc_w_"):].startswith(("first_conv", "second_conv")) else (None, None, None)
+            rest = k[len("enc_w_"):]
+            for pre in ("first_conv", "second_conv"):
+                if rest.startswith(pre + "_"):
+                    idx, name = rest[len(pre) + 1:].split("_", 1)
+                    sd[f"{pre}.{idx}.{name}"] = golden_next[k]
+    return sd
+
+
+def test_encoder_oracle_matches_reference(golden_next):
+    from oracle import np_oracle as no
+    out = no.encoder_eval(golden_next["enc_neighborhood"], _encoder_state_dict(golden_next))
+    want = golden_next["enc_out"]
+    assert np.abs(out - want).max() <= 2e-5 * np.abs(want).max()
