@@ -12,8 +12,10 @@
 // TMEM (tcgen05.ld), bias / ReLU / max applied in registers, and written as BF16 into shared memory in the
 // K-major SWIZZLE_128B canonical layout, where it is the A operand of the next tcgen05.mma.  Weights (BF16,
 // [N][K] = the Conv1d layout) stream from L2 into the same layout in 64-wide K chunks.  FP32 accumulation.
-// This first version is synchronous per K chunk (load, fence, MMA, commit, wait); the structure leaves room
-// for a double-buffered weight pipeline.
+// Weight pieces (one K chunk x up to 256 output channels = 32 KB) travel by cp.async into a two-buffer ring: the
+// copy of piece i+1 overlaps the tcgen05.mma batch of piece i, and a buffer is refilled only after the
+// mbarrier its batch committed to has flipped.  Eight warps: warp w reads TMEM lane quadrant w % 4 (= patch
+// w % 4) and the column half w / 4 of every epilogue.
 //
 // Reference: /root/reference/Point-MAE_SA3D/models/Point_MAE.py:16-47 (Encoder), called at :562 / :1012 with
 // the (B, G, 32, 3) neighbourhood.  Numerics: BF16 operands, FP32 accumulate -> ~1e-2 relative to the FP32
@@ -24,13 +26,14 @@
 
 namespace gm3d {
 
-constexpr int kEncThreads = 128;
+constexpr int kEncThreads = 256;
 constexpr int kEncRows = 128;                 // GEMM M per CTA tile
 constexpr int kChunkK = 64;                   // BF16 elements per 128-byte swizzle row
 constexpr int kAChunkBytes = kEncRows * 128;  // one K chunk of the A operand
 constexpr int kAChunks = 8;                   // K up to 512
-constexpr int kBChunkBytes = 512 * 128;       // one K chunk of up to 512 weight rows
-constexpr size_t kEncSmem = 1024 + kAChunks * kAChunkBytes + kBChunkBytes + 4096;
+constexpr int kBPieceBytes = 256 * 128;       // one weight piece: a K chunk of up to 256 output channels
+constexpr int kBStages = 2;
+constexpr size_t kEncSmem = 1024 + kAChunks * kAChunkBytes + kBStages * kBPieceBytes + 4096;
 
 // byte offset of element (row r, k-in-chunk kk) inside a K-major SWIZZLE_128B chunk (rows x 64 BF16)
 __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t kk) {
@@ -93,15 +96,16 @@ __device__ __forceinline__ float warp_max(float v) {
     return __int_as_float(i);
 }
 
-// stream one K chunk (64 columns starting at k0) of `rows` weight rows (row stride ldw elements) into the B region
-__device__ __forceinline__ void load_b_chunk(unsigned char* sB, const __nv_bfloat16* __restrict__ w, int rows, int ldw, int k0,
-                                             int tid) {
+// cp.async one weight piece -- rows [n0, n0 + rows) x 64 columns from k0 of w (row stride ldw) -- into a B buffer
+__device__ __forceinline__ void load_b_piece(uint32_t sB, const __nv_bfloat16* __restrict__ w, int n0, int rows, int ldw,
+                                             int k0, int tid) {
     const int n16 = rows * 8;  // 16-byte pieces
     for (int t = tid; t < n16; t += kEncThreads) {
         const int r = t >> 3, j = t & 7;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(w + static_cast<size_t>(r) * ldw + k0 + j * 8));
-        *reinterpret_cast<uint4*>(sB + sw128(r, j * 8)) = v;
+        const __nv_bfloat16* src = w + static_cast<size_t>(n0 + r) * ldw + k0 + j * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sB + sw128(r, j * 8)), "l"(src) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 struct EncoderParams {
@@ -121,20 +125,22 @@ struct EncoderParams {
 __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __grid_constant__ EncoderParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
-    unsigned char* sA = base;                               // 8 K chunks of the A operand (1024-byte aligned)
-    unsigned char* sB = base + kAChunks * kAChunkBytes;     // one K chunk of weights
-    float* s_w1 = reinterpret_cast<float*>(sB + kBChunkBytes);  // 128 x 4: w1 rows + b1
-    __shared__ __align__(8) uint64_t s_bar;
+    unsigned char* sA = base;                                        // 8 K chunks of the A operand (1024-byte aligned)
+    unsigned char* sB = base + kAChunks * kAChunkBytes;              // ring of weight pieces
+    float* s_w1 = reinterpret_cast<float*>(sB + kBStages * kBPieceBytes);  // 128 x 4: w1 rows + b1
+    __shared__ __align__(8) uint64_t s_free[kBStages];  // flips when the MMA batch reading that buffer has completed
     __shared__ uint32_t s_tmem;
     __shared__ int s_fail;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int quad = warp & 3, half = warp >> 2;  // TMEM lane quadrant (= patch of the tile) and epilogue column half
+    const int row = quad * 32 + lane;             // GEMM row of this thread's point
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        mbar_init(&s_bar, 1);
+        for (int i = 0; i < kBStages; ++i) mbar_init(&s_free[i], 1);
         mbar_fence_init();
         s_fail = 0;
     }
@@ -146,38 +152,54 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
-    const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);  // this warp's 32 TMEM lanes
+    const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16);  // this warp's 32 TMEM lanes
     const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
-    uint32_t parity = 0;
+    uint32_t uses[kBStages] = {0, 0};  // how many MMA batches have been committed to each buffer (same in every thread)
 
-    // one GEMM: D[128 x N] (TMEM columns [0, N)) = A[128 x 64*kchunks] * W[N x ldw]^T, N issued as 256 + remainder
+    auto wait_free = [&](int bufi) {  // the batch that last read buffer bufi has completed
+        if (uses[bufi] == 0) return;
+        if (!s_fail && !mbar_wait_bounded(&s_free[bufi], (uses[bufi] - 1) & 1)) s_fail = 1;
+    };
+    // one GEMM: D[128 x N] (TMEM columns [0, N)) = A[128 x 64*kchunks] * W[N x ldw]^T.
+    // Pieces p = (K chunk c, N half h); piece p+1 is in flight while the MMAs of piece p run.
     auto gemm = [&](const __nv_bfloat16* w, int N, int kchunks, int ldw) {
-        for (int c = 0; c < kchunks; ++c) {
-            load_b_chunk(sB, w, N, ldw, c * kChunkK, tid);
-            fence_async_smem();
+        const int halves = (N + 255) / 256, np = kchunks * halves;
+        auto issue = [&](int pc) {
+            const int c = pc / halves, h = pc - c * halves;
+            const int n0 = h * 256, rows = N - n0 < 256 ? N - n0 : 256;
+            wait_free(pc & 1);
+            load_b_piece(aB + (pc & 1) * kBPieceBytes, w, n0, rows, ldw, c * kChunkK, tid);
+        };
+        issue(0);
+        for (int pc = 0; pc < np; ++pc) {
+            if (pc + 1 < np) {
+                issue(pc + 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            fence_async_smem();  // this thread's copies (and, for the first piece, its A-operand stores) -> async proxy
             __syncthreads();
+            const int c = pc / halves, h = pc - c * halves;
+            const int n0 = h * 256, rows = N - n0 < 256 ? N - n0 : 256;
             if (tid == 0) {
                 tc_fence_after();
+                const uint32_t idesc = umma_idesc(rows);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t ad = umma_desc(aA + c * kAChunkBytes + ks * 32);
-                    for (int n0 = 0; n0 < N; n0 += 256) {
-                        const int nn = N - n0 < 256 ? N - n0 : 256;
-                        umma_bf16(tmem + n0, ad, umma_desc(aB + (n0 >> 3) * 1024 + ks * 32), umma_idesc(nn), (c | ks) != 0);
-                    }
-                }
-                umma_commit(&s_bar);
+                for (int ks = 0; ks < 4; ++ks)
+                    umma_bf16(tmem + n0, umma_desc(aA + c * kAChunkBytes + ks * 32),
+                              umma_desc(aB + (pc & 1) * kBPieceBytes + ks * 32), idesc, (c | ks) != 0);
+                umma_commit(&s_free[pc & 1]);
             }
-            if (!s_fail && !mbar_wait_bounded(&s_bar, parity)) s_fail = 1;  // (every thread sees the same outcome)
-            parity ^= 1;
-            __syncthreads();  // the B region may be overwritten
+            ++uses[pc & 1];
         }
+        wait_free((np - 1) & 1);  // commits complete in order: every MMA of this GEMM has written TMEM
         tc_fence_after();
     };
 
     const int ntiles = (p.P + 3) / 4;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int patch = tile * 4 + warp;
+        const int patch = tile * 4 + quad;
         const bool live = patch < p.P;
         // ---- layer 1 on the CUDA cores: row = this thread's point
         float x = 0.f, y = 0.f, z = 0.f;
@@ -186,7 +208,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
             x = __ldg(q), y = __ldg(q + 1), z = __ldg(q + 2);
         }
 #pragma unroll 4
-        for (int c0 = 0; c0 < 128; c0 += 8) {
+        for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 8) {  // each column half = one K chunk of H1
             __align__(16) __nv_bfloat162 h[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -196,11 +218,11 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
                 const float hb = fmaxf(fmaf(wb.z, z, fmaf(wb.y, y, fmaf(wb.x, x, wb.w))), 0.f);
                 h[e] = __floats2bfloat162_rn(ha, hb);
             }
-            *reinterpret_cast<uint4*>(sA + (c0 >> 6) * kAChunkBytes + sw128(tid, c0 & 63)) = *reinterpret_cast<const uint4*>(h);
+            *reinterpret_cast<uint4*>(sA + (c0 >> 6) * kAChunkBytes + sw128(row, c0 & 63)) = *reinterpret_cast<const uint4*>(h);
         }
         // ---- layer 2: f = W2 h1 + b2 (N = 256, K = 128); epilogue: F and the patch maximum G as the next A operand
         gemm(p.w2, 256, 2, 128);
-        for (int c0 = 0; c0 < 256; c0 += 16) {
+        for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 16) {
             float v[16];
             tmem_ld16(trow + c0, v);
             __align__(16) __nv_bfloat162 f2[8], g2[8];
@@ -211,15 +233,15 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
                 g2[e >> 1] = __floats2bfloat162_rn(warp_max(fa), warp_max(fb));
             }
             const int ch = c0 >> 6, kk = c0 & 63;
-            *reinterpret_cast<uint4*>(sA + ch * kAChunkBytes + sw128(tid, kk)) = *reinterpret_cast<const uint4*>(f2);
-            *reinterpret_cast<uint4*>(sA + ch * kAChunkBytes + sw128(tid, kk + 8)) = *reinterpret_cast<const uint4*>(f2 + 4);
-            *reinterpret_cast<uint4*>(sA + (4 + ch) * kAChunkBytes + sw128(tid, kk)) = *reinterpret_cast<const uint4*>(g2);
-            *reinterpret_cast<uint4*>(sA + (4 + ch) * kAChunkBytes + sw128(tid, kk + 8)) = *reinterpret_cast<const uint4*>(g2 + 4);
+            *reinterpret_cast<uint4*>(sA + ch * kAChunkBytes + sw128(row, kk)) = *reinterpret_cast<const uint4*>(f2);
+            *reinterpret_cast<uint4*>(sA + ch * kAChunkBytes + sw128(row, kk + 8)) = *reinterpret_cast<const uint4*>(f2 + 4);
+            *reinterpret_cast<uint4*>(sA + (4 + ch) * kAChunkBytes + sw128(row, kk)) = *reinterpret_cast<const uint4*>(g2);
+            *reinterpret_cast<uint4*>(sA + (4 + ch) * kAChunkBytes + sw128(row, kk + 8)) = *reinterpret_cast<const uint4*>(g2 + 4);
         }
         tc_fence_before();
         // ---- layer 3: h2 = relu(W3' [f ; g] + b3') (N = 512, K = 512); epilogue: H2 as the next A operand
         gemm(p.w3, 512, 8, 512);
-        for (int c0 = 0; c0 < 512; c0 += 16) {
+        for (int c0 = half * 256; c0 < half * 256 + 256; c0 += 16) {
             float v[16];
             tmem_ld16(trow + c0, v);
             __align__(16) __nv_bfloat162 h2[8];
@@ -227,13 +249,14 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
             for (int e = 0; e < 16; e += 2)
                 h2[e >> 1] = __floats2bfloat162_rn(fmaxf(v[e] + __ldg(p.b3 + c0 + e), 0.f), fmaxf(v[e + 1] + __ldg(p.b3 + c0 + e + 1), 0.f));
             const int ch = c0 >> 6, kk = c0 & 63;
-            *reinterpret_cast<uint4*>(sA + ch * kAChunkBytes + sw128(tid, kk)) = *reinterpret_cast<const uint4*>(h2);
-            *reinterpret_cast<uint4*>(sA + ch * kAChunkBytes + sw128(tid, kk + 8)) = *reinterpret_cast<const uint4*>(h2 + 4);
+            *reinterpret_cast<uint4*>(sA + ch * kAChunkBytes + sw128(row, kk)) = *reinterpret_cast<const uint4*>(h2);
+            *reinterpret_cast<uint4*>(sA + ch * kAChunkBytes + sw128(row, kk + 8)) = *reinterpret_cast<const uint4*>(h2 + 4);
         }
         tc_fence_before();
         // ---- layer 4: out = max over points (W4 h2 + b4) (N = C, K = 512)
         gemm(p.w4, p.C, 8, 512);
-        for (int c0 = 0; c0 < p.C; c0 += 16) {
+        const int chalf = ((p.C / 16 + 1) / 2) * 16;  // columns of the first half (a multiple of 16)
+        for (int c0 = half ? chalf : 0; c0 < (half ? p.C : chalf); c0 += 16) {
             float v[16];
             tmem_ld16(trow + c0, v);
             float mine = 0.f;

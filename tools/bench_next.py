@@ -91,3 +91,48 @@ def sub():
 us = gpu_us(sub, reps=20)
 print(json.dumps({"op": "fine-tune sub-sampling (FPS 2048 of 2048 + 1024-column gather)", "shape": [32, 2048, 3], "gpu_us": round(us, 1),
                   "clouds_per_s": round(32 / us * 1e6), "cpu_oracle_us": round(cpu_us(lambda: no.gather_points(pts, co.fps(pts, 2048), ch), budget=5.0), 1)}))
+
+# ---- Encoder (mini-PointNet) forward: tcgen05 kernel vs the same module run by PyTorch (library GEMMs)
+from gm3d_b200.encoder import EncoderB200  # noqa: E402
+
+g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "reference_next.npz"))
+sd = {}
+for kname in g.files:
+    if kname.startswith("enc_w_"):
+        rest = kname[len("enc_w_"):]
+        for pre in ("first_conv", "second_conv"):
+            if rest.startswith(pre + "_"):
+                i, nm = rest[len(pre) + 1:].split("_", 1)
+                sd[f"{pre}.{i}.{nm}"] = torch.from_numpy(g[kname])
+enc = EncoderB200.from_state_dict(sd).to(dev)
+import torch.nn as nn  # noqa: E402
+
+
+class TorchEncoder(nn.Module):  # the reference module's structure (models/Point_MAE.py:16-47), library kernels
+    def __init__(self):
+        super().__init__()
+        self.first_conv = nn.Sequential(nn.Conv1d(3, 128, 1), nn.BatchNorm1d(128), nn.ReLU(inplace=True), nn.Conv1d(128, 256, 1))
+        self.second_conv = nn.Sequential(nn.Conv1d(512, 512, 1), nn.BatchNorm1d(512), nn.ReLU(inplace=True), nn.Conv1d(512, 384, 1))
+
+    def forward(self, pg):
+        bs, gg, n, _ = pg.shape
+        f = self.first_conv(pg.reshape(bs * gg, n, 3).transpose(2, 1))
+        fg = torch.max(f, dim=2, keepdim=True)[0]
+        f = self.second_conv(torch.cat([fg.expand(-1, -1, n), f], dim=1))
+        return torch.max(f, dim=2)[0].reshape(bs, gg, 384)
+
+
+ref = TorchEncoder().to(dev).eval()
+ref.load_state_dict(sd)
+for B_, G_ in ((128, 64), (32, 128)):
+    nb = (torch.randn(B_, G_, 32, 3, device=dev) * 0.08)
+    P_ = B_ * G_
+    flop = 2.0 * 32 * (3 * 128 + 128 * 256 + 512 * 512 + 512 * 384) * P_
+    us = gpu_us(lambda: enc(nb), reps=20)
+    with torch.no_grad():
+        us32 = gpu_us(lambda: ref(nb), reps=20)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            us16 = gpu_us(lambda: ref(nb), reps=20)
+    print(json.dumps({"op": "Encoder forward (eval)", "patches": P_, "gpu_us": round(us, 1), "tflops": round(flop / us / 1e6, 1),
+                      "frac_of_measured_bf16_peak": round(flop / us / 1e6 / 1668.9, 4), "patches_per_s": round(P_ / us * 1e6),
+                      "torch_fp32_us": round(us32, 1), "torch_bf16_autocast_us": round(us16, 1)}))
