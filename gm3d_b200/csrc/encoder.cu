@@ -12,10 +12,12 @@
 // TMEM (tcgen05.ld), bias / ReLU / max applied in registers, and written as BF16 into shared memory in the
 // K-major SWIZZLE_128B canonical layout, where it is the A operand of the next tcgen05.mma.  Weights (BF16,
 // [N][K] = the Conv1d layout) stream from L2 into the same layout in 64-wide K chunks.  FP32 accumulation.
-// Weight pieces (one K chunk x up to 256 output channels = 32 KB) travel by cp.async into a two-buffer ring: the
-// copy of piece i+1 overlaps the tcgen05.mma batch of piece i, and a buffer is refilled only after the
-// mbarrier its batch committed to has flipped.  Eight warps: warp w reads TMEM lane quadrant w % 4 (= patch
-// w % 4) and the column half w / 4 of every epilogue.
+// Warp-specialised: warp 8 lane 0 is the weight producer -- the caller stores the weights PRE-TILED as the 16 KB
+// swizzled shared-memory images of (K chunk, 128-channel slice) pieces, so one 1-D bulk copy (TMA engine,
+// mbarrier complete_tx) per piece fills a stage of a four-deep ring; warp 9 lane 0 issues the tcgen05.mma
+// batches as stages fill and commits each batch to the stage's "empty" mbarrier; warps 0..7 compute layer 1 and
+// run the epilogues (warp w: TMEM lane quadrant w % 4 = patch w % 4, column half w / 4).  Nothing but mbarriers
+// synchronises the roles; the producer runs ahead across layers and tiles, so L2 latency hides under the epilogues.
 //
 // Reference: /root/reference/Point-MAE_SA3D/models/Point_MAE.py:16-47 (Encoder), called at :562 / :1012 with
 // the (B, G, 32, 3) neighbourhood.  Numerics: BF16 operands, FP32 accumulate -> ~1e-2 relative to the FP32
@@ -26,13 +28,15 @@
 
 namespace gm3d {
 
-constexpr int kEncThreads = 256;
+constexpr int kEpiThreads = 256;              // warps 0..7: layer 1 + epilogues
+constexpr int kEncThreads = kEpiThreads + 64;  // + producer warp + MMA warp
 constexpr int kEncRows = 128;                 // GEMM M per CTA tile
 constexpr int kChunkK = 64;                   // BF16 elements per 128-byte swizzle row
 constexpr int kAChunkBytes = kEncRows * 128;  // one K chunk of the A operand
 constexpr int kAChunks = 8;                   // K up to 512
-constexpr int kBPieceBytes = 256 * 128;       // one weight piece: a K chunk of up to 256 output channels
-constexpr int kBStages = 2;
+constexpr int kPieceN = 128;                  // output channels per weight piece
+constexpr int kBPieceBytes = kPieceN * 128;   // one weight piece: a K chunk (64) of 128 output channels = 16 KB
+constexpr int kBStages = 4;                   // ring depth: three pieces in flight ahead of the MMAs
 constexpr size_t kEncSmem = 1024 + kAChunks * kAChunkBytes + kBStages * kBPieceBytes + 4096;
 
 // byte offset of element (row r, k-in-chunk kk) inside a K-major SWIZZLE_128B chunk (rows x 64 BF16)
@@ -96,23 +100,11 @@ __device__ __forceinline__ float warp_max(float v) {
     return __int_as_float(i);
 }
 
-// cp.async one weight piece -- rows [n0, n0 + rows) x 64 columns from k0 of w (row stride ldw) -- into a B buffer
-__device__ __forceinline__ void load_b_piece(uint32_t sB, const __nv_bfloat16* __restrict__ w, int n0, int rows, int ldw,
-                                             int k0, int tid) {
-    const int n16 = rows * 8;  // 16-byte pieces
-    for (int t = tid; t < n16; t += kEncThreads) {
-        const int r = t >> 3, j = t & 7;
-        const __nv_bfloat16* src = w + static_cast<size_t>(n0 + r) * ldw + k0 + j * 8;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sB + sw128(r, j * 8)), "l"(src) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
 struct EncoderParams {
     const float* nbhd;  // (P, 32, 3)
     int P, C;
     const float *w1, *b1;        // (128, 3), (128): BatchNorm folded
-    const __nv_bfloat16* w2;     // (256, 128)
+    const __nv_bfloat16* w2;     // (256, 128)   -- all three pre-tiled: piece (c, q) = 16 KB image at (c * slices + q) * 16 KB
     const float* b2;             // (256)
     const __nv_bfloat16* w3;     // (512, 512): BatchNorm folded, input columns ordered [f (256) ; g (256)]
     const float* b3;             // (512)
@@ -128,19 +120,22 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
     unsigned char* sA = base;                                        // 8 K chunks of the A operand (1024-byte aligned)
     unsigned char* sB = base + kAChunks * kAChunkBytes;              // ring of weight pieces
     float* s_w1 = reinterpret_cast<float*>(sB + kBStages * kBPieceBytes);  // 128 x 4: w1 rows + b1
-    __shared__ __align__(8) uint64_t s_free[kBStages];  // flips when the MMA batch reading that buffer has completed
+    __shared__ __align__(8) uint64_t s_full[kBStages];   // producer -> MMA: the piece has landed (complete_tx)
+    __shared__ __align__(8) uint64_t s_empty[kBStages];  // MMA -> producer: the batch reading the stage has completed
+    __shared__ __align__(8) uint64_t s_aready;           // epilogue threads -> MMA: the A operand of the next GEMM is written
+    __shared__ __align__(8) uint64_t s_done;             // MMA -> epilogue: every MMA of the GEMM has written TMEM
     __shared__ uint32_t s_tmem;
     __shared__ int s_fail;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int quad = warp & 3, half = warp >> 2;  // TMEM lane quadrant (= patch of the tile) and epilogue column half
-    const int row = quad * 32 + lane;             // GEMM row of this thread's point
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int i = 0; i < kBStages; ++i) mbar_init(&s_free[i], 1);
+        for (int i = 0; i < kBStages; ++i) mbar_init(&s_full[i], 1), mbar_init(&s_empty[i], 1);
+        mbar_init(&s_aready, kEpiThreads);
+        mbar_init(&s_done, 1);
         mbar_fence_init();
         s_fail = 0;
     }
@@ -152,127 +147,149 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
-    const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16);  // this warp's 32 TMEM lanes
     const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
-    uint32_t uses[kBStages] = {0, 0};  // how many MMA batches have been committed to each buffer (same in every thread)
-
-    auto wait_free = [&](int bufi) {  // the batch that last read buffer bufi has completed
-        if (uses[bufi] == 0) return;
-        if (!s_fail && !mbar_wait_bounded(&s_free[bufi], (uses[bufi] - 1) & 1)) s_fail = 1;
-    };
-    // one GEMM: D[128 x N] (TMEM columns [0, N)) = A[128 x 64*kchunks] * W[N x ldw]^T.
-    // Pieces p = (K chunk c, N half h); piece p+1 is in flight while the MMAs of piece p run.
-    auto gemm = [&](const __nv_bfloat16* w, int N, int kchunks, int ldw) {
-        const int halves = (N + 255) / 256, np = kchunks * halves;
-        auto issue = [&](int pc) {
-            const int c = pc / halves, h = pc - c * halves;
-            const int n0 = h * 256, rows = N - n0 < 256 ? N - n0 : 256;
-            wait_free(pc & 1);
-            load_b_piece(aB + (pc & 1) * kBPieceBytes, w, n0, rows, ldw, c * kChunkK, tid);
-        };
-        issue(0);
-        for (int pc = 0; pc < np; ++pc) {
-            if (pc + 1 < np) {
-                issue(pc + 1);
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
-            } else {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-            }
-            fence_async_smem();  // this thread's copies (and, for the first piece, its A-operand stores) -> async proxy
-            __syncthreads();
-            const int c = pc / halves, h = pc - c * halves;
-            const int n0 = h * 256, rows = N - n0 < 256 ? N - n0 : 256;
-            if (tid == 0) {
-                tc_fence_after();
-                const uint32_t idesc = umma_idesc(rows);
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    umma_bf16(tmem + n0, umma_desc(aA + c * kAChunkBytes + ks * 32),
-                              umma_desc(aB + (pc & 1) * kBPieceBytes + ks * 32), idesc, (c | ks) != 0);
-                umma_commit(&s_free[pc & 1]);
-            }
-            ++uses[pc & 1];
-        }
-        wait_free((np - 1) & 1);  // commits complete in order: every MMA of this GEMM has written TMEM
-        tc_fence_after();
-    };
-
     const int ntiles = (p.P + 3) / 4;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int patch = tile * 4 + quad;
-        const bool live = patch < p.P;
-        // ---- layer 1 on the CUDA cores: row = this thread's point
-        float x = 0.f, y = 0.f, z = 0.f;
-        if (live) {
-            const float* q = p.nbhd + (static_cast<size_t>(patch) * 32 + lane) * 3;
-            x = __ldg(q), y = __ldg(q + 1), z = __ldg(q + 2);
+    const int slices4 = (p.C + kPieceN - 1) / kPieceN;
+    // the three GEMMs of a tile: weights, N, K chunks
+    const __nv_bfloat16* const gw[3] = {p.w2, p.w3, p.w4};
+    const int gN[3] = {256, 512, p.C}, gK[3] = {2, 8, 8}, gS[3] = {2, 4, slices4};
+    auto wait = [&](uint64_t* bar, uint32_t parity) {
+        if (!s_fail && !mbar_wait_bounded(bar, parity)) s_fail = 1;
+    };
+
+    if (warp == 8) {
+        // ===== weight producer: one bulk copy per piece, as far ahead as the ring allows
+        if (lane == 0) {
+            uint32_t cnt = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+                for (int g = 0; g < 3; ++g) {
+                    const unsigned char* src = reinterpret_cast<const unsigned char*>(gw[g]);
+                    const int np = gK[g] * gS[g];
+                    for (int pc = 0; pc < np; ++pc, ++cnt) {
+                        const int st = cnt % kBStages;
+                        if (cnt >= kBStages) wait(&s_empty[st], (cnt / kBStages - 1) & 1);
+                        mbar_arrive_expect_tx(&s_full[st], kBPieceBytes);
+                        bulk_g2s(sB + st * kBPieceBytes, src + static_cast<size_t>(pc) * kBPieceBytes, kBPieceBytes, &s_full[st]);
+                    }
+                }
         }
+    } else if (warp == 9) {
+        // ===== MMA issuer
+        if (lane == 0) {
+            uint32_t cnt = 0, gi = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+                for (int g = 0; g < 3; ++g, ++gi) {
+                    wait(&s_aready, gi & 1);  // A operand written (and the previous accumulator drained)
+                    tc_fence_after();
+                    const int N = gN[g], slices = gS[g], np = gK[g] * slices;
+                    for (int pc = 0; pc < np; ++pc, ++cnt) {
+                        const int st = cnt % kBStages;
+                        const int c = pc / slices, q = pc - c * slices;
+                        const int n0 = q * kPieceN, rows = N - n0 < kPieceN ? N - n0 : kPieceN;
+                        wait(&s_full[st], (cnt / kBStages) & 1);
+                        tc_fence_after();
+                        const uint32_t idesc = umma_idesc(rows);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_bf16(tmem + n0, umma_desc(aA + c * kAChunkBytes + ks * 32),
+                                      umma_desc(aB + st * kBPieceBytes + ks * 32), idesc, (c | ks) != 0);
+                        umma_commit(&s_empty[st]);
+                    }
+                    umma_commit(&s_done);  // completes after every MMA issued so far
+                }
+        }
+    } else {
+        // ===== layer 1 + epilogues
+        const int quad = warp & 3, half = warp >> 2;  // TMEM lane quadrant (= patch of the tile), epilogue column half
+        const int row = quad * 32 + lane;             // GEMM row of this thread's point
+        const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+        uint32_t gi = 0;
+        auto a_written = [&]() {  // this thread's A-operand stores are visible to the async proxy; TMEM reads are done
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(&s_aready);
+        };
+        auto gemm_done = [&]() {
+            wait(&s_done, gi & 1);
+            ++gi;
+            tc_fence_after();
+        };
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int patch = tile * 4 + quad;
+            const bool live = patch < p.P;
+            // ---- layer 1 on the CUDA cores (each column half = one K chunk of H1)
+            float x = 0.f, y = 0.f, z = 0.f;
+            if (live) {
+                const float* q = p.nbhd + (static_cast<size_t>(patch) * 32 + lane) * 3;
+                x = __ldg(q), y = __ldg(q + 1), z = __ldg(q + 2);
+            }
 #pragma unroll 4
-        for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 8) {  // each column half = one K chunk of H1
-            __align__(16) __nv_bfloat162 h[4];
+            for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 8) {
+                __align__(16) __nv_bfloat162 h[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float4 wa = *reinterpret_cast<const float4*>(s_w1 + 4 * (c0 + 2 * e));
-                const float4 wb = *reinterpret_cast<const float4*>(s_w1 + 4 * (c0 + 2 * e + 1));
-                const float ha = fmaxf(fmaf(wa.z, z, fmaf(wa.y, y, fmaf(wa.x, x, wa.w))), 0.f);
-                const float hb = fmaxf(fmaf(wb.z, z, fmaf(wb.y, y, fmaf(wb.x, x, wb.w))), 0.f);
-                h[e] = __floats2bfloat162_rn(ha, hb);
+                for (int e = 0; e < 4; ++e) {
+                    const float4 wa = *reinterpret_cast<const float4*>(s_w1 + 4 * (c0 + 2 * e));
+                    const float4 wb = *reinterpret_cast<const float4*>(s_w1 + 4 * (c0 + 2 * e + 1));
+                    const float ha = fmaxf(fmaf(wa.z, z, fmaf(wa.y, y, fmaf(wa.x, x, wa.w))), 0.f);
+                    const float hb = fmaxf(fmaf(wb.z, z, fmaf(wb.y, y, fmaf(wb.x, x, wb.w))), 0.f);
+                    h[e] = __floats2bfloat162_rn(ha, hb);
+                }
+                *reinterpret_cast<uint4*>(sA + (c0 >> 6) * kAChunkBytes + sw128(row, c0 & 63)) = *reinterpret_cast<const uint4*>(h);
             }
-            *reinterpret_cast<uint4*>(sA + (c0 >> 6) * kAChunkBytes + sw128(row, c0 & 63)) = *reinterpret_cast<const uint4*>(h);
-        }
-        // ---- layer 2: f = W2 h1 + b2 (N = 256, K = 128); epilogue: F and the patch maximum G as the next A operand
-        gemm(p.w2, 256, 2, 128);
-        for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 16) {
-            float v[16];
-            tmem_ld16(trow + c0, v);
-            __align__(16) __nv_bfloat162 f2[8], g2[8];
+            a_written();
+            // ---- layer 2 epilogue: f = acc + b2 -> F, patch maximum -> G (the next A operand is [F ; G])
+            gemm_done();
+            for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 16) {
+                float v[16];
+                tmem_ld16(trow + c0, v);
+                __align__(16) __nv_bfloat162 f2[8], g2[8];
 #pragma unroll
-            for (int e = 0; e < 16; e += 2) {
-                const float fa = v[e] + __ldg(p.b2 + c0 + e), fb = v[e + 1] + __ldg(p.b2 + c0 + e + 1);
-                f2[e >> 1] = __floats2bfloat162_rn(fa, fb);
-                g2[e >> 1] = __floats2bfloat162_rn(warp_max(fa), warp_max(fb));
+                for (int e = 0; e < 16; e += 2) {
+                    const float fa = v[e] + __ldg(p.b2 + c0 + e), fb = v[e + 1] + __ldg(p.b2 + c0 + e + 1);
+                    f2[e >> 1] = __floats2bfloat162_rn(fa, fb);
+                    g2[e >> 1] = __floats2bfloat162_rn(warp_max(fa), warp_max(fb));
+                }
+                const int ch = c0 >> 6, kk = c0 & 63;
+                *reinterpret_cast<uint4*>(sA + ch * kAChunkBytes + sw128(row, kk)) = *reinterpret_cast<const uint4*>(f2);
+                *reinterpret_cast<uint4*>(sA + ch * kAChunkBytes + sw128(row, kk + 8)) = *reinterpret_cast<const uint4*>(f2 + 4);
+                *reinterpret_cast<uint4*>(sA + (4 + ch) * kAChunkBytes + sw128(row, kk)) = *reinterpret_cast<const uint4*>(g2);
+                *reinterpret_cast<uint4*>(sA + (4 + ch) * kAChunkBytes + sw128(row, kk + 8)) = *reinterpret_cast<const uint4*>(g2 + 4);
             }
-            const int ch = c0 >> 6, kk = c0 & 63;
-            *reinterpret_cast<uint4*>(sA + ch * kAChunkBytes + sw128(row, kk)) = *reinterpret_cast<const uint4*>(f2);
-            *reinterpret_cast<uint4*>(sA + ch * kAChunkBytes + sw128(row, kk + 8)) = *reinterpret_cast<const uint4*>(f2 + 4);
-            *reinterpret_cast<uint4*>(sA + (4 + ch) * kAChunkBytes + sw128(row, kk)) = *reinterpret_cast<const uint4*>(g2);
-            *reinterpret_cast<uint4*>(sA + (4 + ch) * kAChunkBytes + sw128(row, kk + 8)) = *reinterpret_cast<const uint4*>(g2 + 4);
-        }
-        tc_fence_before();
-        // ---- layer 3: h2 = relu(W3' [f ; g] + b3') (N = 512, K = 512); epilogue: H2 as the next A operand
-        gemm(p.w3, 512, 8, 512);
-        for (int c0 = half * 256; c0 < half * 256 + 256; c0 += 16) {
-            float v[16];
-            tmem_ld16(trow + c0, v);
-            __align__(16) __nv_bfloat162 h2[8];
+            a_written();
+            // ---- layer 3 epilogue: h2 = relu(acc + b3') -> the next A operand
+            gemm_done();
+            for (int c0 = half * 256; c0 < half * 256 + 256; c0 += 16) {
+                float v[16];
+                tmem_ld16(trow + c0, v);
+                __align__(16) __nv_bfloat162 h2[8];
 #pragma unroll
-            for (int e = 0; e < 16; e += 2)
-                h2[e >> 1] = __floats2bfloat162_rn(fmaxf(v[e] + __ldg(p.b3 + c0 + e), 0.f), fmaxf(v[e + 1] + __ldg(p.b3 + c0 + e + 1), 0.f));
-            const int ch = c0 >> 6, kk = c0 & 63;
-            *reinterpret_cast<uint4*>(sA + ch * kAChunkBytes + sw128(row, kk)) = *reinterpret_cast<const uint4*>(h2);
-            *reinterpret_cast<uint4*>(sA + ch * kAChunkBytes + sw128(row, kk + 8)) = *reinterpret_cast<const uint4*>(h2 + 4);
-        }
-        tc_fence_before();
-        // ---- layer 4: out = max over points (W4 h2 + b4) (N = C, K = 512)
-        gemm(p.w4, p.C, 8, 512);
-        const int chalf = ((p.C / 16 + 1) / 2) * 16;  // columns of the first half (a multiple of 16)
-        for (int c0 = half ? chalf : 0; c0 < (half ? p.C : chalf); c0 += 16) {
-            float v[16];
-            tmem_ld16(trow + c0, v);
-            float mine = 0.f;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const float m = warp_max(v[e]) + __ldg(p.b4 + c0 + e);  // the bias is constant over the points
-                if (lane == e) mine = m;
+                for (int e = 0; e < 16; e += 2)
+                    h2[e >> 1] = __floats2bfloat162_rn(fmaxf(v[e] + __ldg(p.b3 + c0 + e), 0.f), fmaxf(v[e + 1] + __ldg(p.b3 + c0 + e + 1), 0.f));
+                const int ch = c0 >> 6, kk = c0 & 63;
+                *reinterpret_cast<uint4*>(sA + ch * kAChunkBytes + sw128(row, kk)) = *reinterpret_cast<const uint4*>(h2);
+                *reinterpret_cast<uint4*>(sA + ch * kAChunkBytes + sw128(row, kk + 8)) = *reinterpret_cast<const uint4*>(h2 + 4);
             }
-            if (live && lane < 16) p.out[static_cast<size_t>(patch) * p.C + c0 + lane] = mine;
+            a_written();
+            // ---- layer 4 epilogue: out = max over the points (acc) + b4
+            gemm_done();
+            const int chalf = ((p.C / 16 + 1) / 2) * 16;  // columns of the first half (a multiple of 16)
+            for (int c0 = half ? chalf : 0; c0 < (half ? p.C : chalf); c0 += 16) {
+                float v[16];
+                tmem_ld16(trow + c0, v);
+                float mine = 0.f;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const float m = warp_max(v[e]) + __ldg(p.b4 + c0 + e);  // the bias is constant over the points
+                    if (lane == e) mine = m;
+                }
+                if (live && lane < 16) p.out[static_cast<size_t>(patch) * p.C + c0 + lane] = mine;
+            }
+            // (the next tile's layer-1 a_written() tells the MMA warp that these TMEM reads are done)
         }
-        tc_fence_before();
-        __syncthreads();  // TMEM and the A region are free for the next tile
-        tc_fence_after();
     }
-    if (tid == 0 && s_fail && p.status) atomicExch(p.status, 1);
+    tc_fence_before();
     __syncthreads();
+    if (tid == 0 && s_fail && p.status) atomicExch(p.status, 1);
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
@@ -284,7 +301,7 @@ GM3D_API int gm3d_encoder_fwd_bf16(const float* nbhd, int P, int n_points, const
     using namespace gm3d;
     if (!nbhd || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !w4 || !b4 || !out || P <= 0) return GM3D_EINVAL;
     if (n_points != 32) return GM3D_ENOSUP;             // one warp per patch: TMEM lane == point
-    if (C <= 0 || C > 512 || C % 16 != 0) return GM3D_ENOSUP;
+    if (C <= 0 || C > 512 || C % 16 != 0) return GM3D_ENOSUP;  // (w4 pre-tiled in 128-channel slices, zero-padded)
     if ((reinterpret_cast<uintptr_t>(w2) | reinterpret_cast<uintptr_t>(w3) | reinterpret_cast<uintptr_t>(w4)) & 15) return GM3D_EALIGN;
     EncoderParams p{};
     p.nbhd = nbhd, p.P = P, p.C = C, p.w1 = w1, p.b1 = b1, p.b2 = b2, p.b3 = b3, p.b4 = b4, p.out = out, p.status = status;
