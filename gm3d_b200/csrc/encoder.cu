@@ -23,6 +23,7 @@
 // the (B, G, 32, 3) neighbourhood.  Numerics: BF16 operands, FP32 accumulate -> ~1e-2 relative to the FP32
 // reference (the reference itself runs this module under fp16 autocast).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -112,6 +113,7 @@ struct EncoderParams {
     const float* b4;             // (C)
     float* out;                  // (P, C)
     int* status;                 // set to 1 if an MMA never completed
+    int dbg;                     // tuning aid (GM3D_ENC_DBG): 1 = no weight copies, 2 = no epilogue work, 3 = no MMAs
 };
 
 __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __grid_constant__ EncoderParams p) {
@@ -149,10 +151,10 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
     const uint32_t tmem = s_tmem;
     const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
     const int ntiles = (p.P + 3) / 4;
-    const int slices4 = (p.C + kPieceN - 1) / kPieceN;
+    const int slices4 = ((p.C + 2 * kPieceN - 1) / (2 * kPieceN)) * 2;  // w4 is tiled in pairs of 128-channel slices (zero-padded)
     // the three GEMMs of a tile: weights, N, K chunks
     const __nv_bfloat16* const gw[3] = {p.w2, p.w3, p.w4};
-    const int gN[3] = {256, 512, p.C}, gK[3] = {2, 8, 8}, gS[3] = {2, 4, slices4};
+    const int gK[3] = {2, 8, 8}, gS[3] = {2, 4, slices4};
     auto wait = [&](uint64_t* bar, uint32_t parity) {
         if (!s_fail && !mbar_wait_bounded(bar, parity)) s_fail = 1;
     };
@@ -168,6 +170,10 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
                     for (int pc = 0; pc < np; ++pc, ++cnt) {
                         const int st = cnt % kBStages;
                         if (cnt >= kBStages) wait(&s_empty[st], (cnt / kBStages - 1) & 1);
+                        if (p.dbg == 1) {
+                            mbar_arrive(&s_full[st]);
+                            continue;
+                        }
                         mbar_arrive_expect_tx(&s_full[st], kBPieceBytes);
                         bulk_g2s(sB + st * kBPieceBytes, src + static_cast<size_t>(pc) * kBPieceBytes, kBPieceBytes, &s_full[st]);
                     }
@@ -181,19 +187,22 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
                 for (int g = 0; g < 3; ++g, ++gi) {
                     wait(&s_aready, gi & 1);  // A operand written (and the previous accumulator drained)
                     tc_fence_after();
-                    const int N = gN[g], slices = gS[g], np = gK[g] * slices;
-                    for (int pc = 0; pc < np; ++pc, ++cnt) {
-                        const int st = cnt % kBStages;
+                    const int slices = gS[g], np = gK[g] * slices;  // slices is even: pieces pair up into N = 256 batches
+                    for (int pc = 0; pc < np; pc += 2, cnt += 2) {
+                        const int st = cnt % kBStages;  // even: the pair occupies stages st, st + 1 = one 256-row image
                         const int c = pc / slices, q = pc - c * slices;
-                        const int n0 = q * kPieceN, rows = N - n0 < kPieceN ? N - n0 : kPieceN;
                         wait(&s_full[st], (cnt / kBStages) & 1);
+                        wait(&s_full[st + 1], (cnt / kBStages) & 1);
                         tc_fence_after();
-                        const uint32_t idesc = umma_idesc(rows);
+                        const uint32_t idesc = umma_idesc(2 * kPieceN);
+                        if (p.dbg != 3) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            umma_bf16(tmem + n0, umma_desc(aA + c * kAChunkBytes + ks * 32),
-                                      umma_desc(aB + st * kBPieceBytes + ks * 32), idesc, (c | ks) != 0);
+                            for (int ks = 0; ks < 4; ++ks)
+                                umma_bf16(tmem + q * kPieceN, umma_desc(aA + c * kAChunkBytes + ks * 32),
+                                          umma_desc(aB + st * kBPieceBytes + ks * 32), idesc, (c | ks) != 0);
+                        }
                         umma_commit(&s_empty[st]);
+                        umma_commit(&s_empty[st + 1]);
                     }
                     umma_commit(&s_done);  // completes after every MMA issued so far
                 }
@@ -239,7 +248,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
             a_written();
             // ---- layer 2 epilogue: f = acc + b2 -> F, patch maximum -> G (the next A operand is [F ; G])
             gemm_done();
-            for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 16) {
+            for (int c0 = half * 128; c0 < half * 128 + 128 && p.dbg != 2; c0 += 16) {
                 float v[16];
                 tmem_ld16(trow + c0, v);
                 __align__(16) __nv_bfloat162 f2[8], g2[8];
@@ -258,7 +267,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
             a_written();
             // ---- layer 3 epilogue: h2 = relu(acc + b3') -> the next A operand
             gemm_done();
-            for (int c0 = half * 256; c0 < half * 256 + 256; c0 += 16) {
+            for (int c0 = half * 256; c0 < half * 256 + 256 && p.dbg != 2; c0 += 16) {
                 float v[16];
                 tmem_ld16(trow + c0, v);
                 __align__(16) __nv_bfloat162 h2[8];
@@ -273,7 +282,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
             // ---- layer 4 epilogue: out = max over the points (acc) + b4
             gemm_done();
             const int chalf = ((p.C / 16 + 1) / 2) * 16;  // columns of the first half (a multiple of 16)
-            for (int c0 = half ? chalf : 0; c0 < (half ? p.C : chalf); c0 += 16) {
+            for (int c0 = half ? chalf : 0; c0 < (half ? p.C : chalf) && p.dbg != 2; c0 += 16) {
                 float v[16];
                 tmem_ld16(trow + c0, v);
                 float mine = 0.f;
@@ -307,6 +316,8 @@ GM3D_API int gm3d_encoder_fwd_bf16(const float* nbhd, int P, int n_points, const
     p.nbhd = nbhd, p.P = P, p.C = C, p.w1 = w1, p.b1 = b1, p.b2 = b2, p.b3 = b3, p.b4 = b4, p.out = out, p.status = status;
     p.w2 = static_cast<const __nv_bfloat16*>(w2), p.w3 = static_cast<const __nv_bfloat16*>(w3);
     p.w4 = static_cast<const __nv_bfloat16*>(w4);
+    static const int dbg = getenv("GM3D_ENC_DBG") ? atoi(getenv("GM3D_ENC_DBG")) : 0;
+    p.dbg = dbg;
     cudaError_t e = cudaFuncSetAttribute(encoder_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kEncSmem));
     if (e != cudaSuccess) return static_cast<int>(e);
     int dev = 0, sms = 148;
