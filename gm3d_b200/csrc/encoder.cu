@@ -12,11 +12,11 @@
 // TMEM (tcgen05.ld), bias / ReLU / max applied in registers, and written as BF16 into shared memory in the
 // K-major SWIZZLE_128B canonical layout, where it is the A operand of the next tcgen05.mma.  Weights (BF16,
 // [N][K] = the Conv1d layout) stream from L2 into the same layout in 64-wide K chunks.  FP32 accumulation.
-// Warp-specialised: warp 8 lane 0 is the weight producer -- the caller stores the weights PRE-TILED as the 16 KB
+// Warp-specialised: warp 16 lane 0 is the weight producer -- the caller stores the weights PRE-TILED as the 16 KB
 // swizzled shared-memory images of (K chunk, 128-channel slice) pieces, so one 1-D bulk copy (TMA engine,
-// mbarrier complete_tx) per piece fills a stage of a four-deep ring; warp 9 lane 0 issues the tcgen05.mma
-// batches as stages fill and commits each batch to the stage's "empty" mbarrier; warps 0..7 compute layer 1 and
-// run the epilogues (warp w: TMEM lane quadrant w % 4 = patch w % 4, column half w / 4).  Nothing but mbarriers
+// mbarrier complete_tx) per piece fills a stage of a four-deep ring; warp 17 lane 0 issues the tcgen05.mma
+// batches as stages fill and commits each batch to the stage's "empty" mbarrier; warps 0..15 compute layer 1 and
+// run the epilogues (warp w: TMEM lane quadrant w % 4 = patch w % 4, column quarter w / 4).  Nothing but mbarriers
 // synchronises the roles; the producer runs ahead across layers and tiles, so L2 latency hides under the epilogues.
 //
 // Reference: /root/reference/Point-MAE_SA3D/models/Point_MAE.py:16-47 (Encoder), called at :562 / :1012 with
@@ -29,7 +29,8 @@
 
 namespace gm3d {
 
-constexpr int kEpiThreads = 256;              // warps 0..7: layer 1 + epilogues
+constexpr int kEpiWarps = 16;                 // layer 1 + epilogues: warp w -> TMEM lane quadrant w % 4, column quarter w / 4
+constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kEncThreads = kEpiThreads + 64;  // + producer warp + MMA warp
 constexpr int kEncRows = 128;                 // GEMM M per CTA tile
 constexpr int kChunkK = 64;                   // BF16 elements per 128-byte swizzle row
@@ -38,7 +39,8 @@ constexpr int kAChunks = 8;                   // K up to 512
 constexpr int kPieceN = 128;                  // output channels per weight piece
 constexpr int kBPieceBytes = kPieceN * 128;   // one weight piece: a K chunk (64) of 128 output channels = 16 KB
 constexpr int kBStages = 4;                   // ring depth: three pieces in flight ahead of the MMAs
-constexpr size_t kEncSmem = 1024 + kAChunks * kAChunkBytes + kBStages * kBPieceBytes + 4096;
+constexpr int kBiasFloats = 256 + 512 + 512;  // b2, b3, b4 cached in shared memory
+constexpr size_t kEncSmem = 1024 + kAChunks * kAChunkBytes + kBStages * kBPieceBytes + 2048 + kBiasFloats * 4;
 
 // byte offset of element (row r, k-in-chunk kk) inside a K-major SWIZZLE_128B chunk (rows x 64 BF16)
 __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t kk) {
@@ -122,6 +124,9 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
     unsigned char* sA = base;                                        // 8 K chunks of the A operand (1024-byte aligned)
     unsigned char* sB = base + kAChunks * kAChunkBytes;              // ring of weight pieces
     float* s_w1 = reinterpret_cast<float*>(sB + kBStages * kBPieceBytes);  // 128 x 4: w1 rows + b1
+    float* s_b2 = s_w1 + 512;                                              // 256, then b3 (512), b4 (C <= 512)
+    float* s_b3 = s_b2 + 256;
+    float* s_b4 = s_b3 + 512;
     __shared__ __align__(8) uint64_t s_full[kBStages];   // producer -> MMA: the piece has landed (complete_tx)
     __shared__ __align__(8) uint64_t s_empty[kBStages];  // MMA -> producer: the batch reading the stage has completed
     __shared__ __align__(8) uint64_t s_aready;           // epilogue threads -> MMA: the A operand of the next GEMM is written
@@ -145,13 +150,16 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
         s_w1[4 * c + 0] = p.w1[3 * c + 0], s_w1[4 * c + 1] = p.w1[3 * c + 1], s_w1[4 * c + 2] = p.w1[3 * c + 2];
         s_w1[4 * c + 3] = p.b1[c];
     }
+    for (int c = tid; c < 256; c += kEncThreads) s_b2[c] = p.b2[c];
+    for (int c = tid; c < 512; c += kEncThreads) s_b3[c] = p.b3[c];
+    for (int c = tid; c < p.C; c += kEncThreads) s_b4[c] = p.b4[c];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
     const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
     const int ntiles = (p.P + 3) / 4;
-    const int slices4 = ((p.C + 2 * kPieceN - 1) / (2 * kPieceN)) * 2;  // w4 is tiled in pairs of 128-channel slices (zero-padded)
+    const int slices4 = (p.C + kPieceN - 1) / kPieceN;  // w4 is tiled in 128-channel slices (zero-padded)
     // the three GEMMs of a tile: weights, N, K chunks
     const __nv_bfloat16* const gw[3] = {p.w2, p.w3, p.w4};
     const int gK[3] = {2, 8, 8}, gS[3] = {2, 4, slices4};
@@ -159,7 +167,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
         if (!s_fail && !mbar_wait_bounded(bar, parity)) s_fail = 1;
     };
 
-    if (warp == 8) {
+    if (warp == kEpiWarps) {
         // ===== weight producer: one bulk copy per piece, as far ahead as the ring allows
         if (lane == 0) {
             uint32_t cnt = 0;
@@ -179,7 +187,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
                     }
                 }
         }
-    } else if (warp == 9) {
+    } else if (warp == kEpiWarps + 1) {
         // ===== MMA issuer
         if (lane == 0) {
             uint32_t cnt = 0, gi = 0;
@@ -187,14 +195,16 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
                 for (int g = 0; g < 3; ++g, ++gi) {
                     wait(&s_aready, gi & 1);  // A operand written (and the previous accumulator drained)
                     tc_fence_after();
-                    const int slices = gS[g], np = gK[g] * slices;  // slices is even: pieces pair up into N = 256 batches
-                    for (int pc = 0; pc < np; pc += 2, cnt += 2) {
-                        const int st = cnt % kBStages;  // even: the pair occupies stages st, st + 1 = one 256-row image
+                    const int slices = gS[g], np = gK[g] * slices;
+                    for (int pc = 0; pc < np;) {
+                        const int st = cnt % kBStages;
                         const int c = pc / slices, q = pc - c * slices;
+                        // two neighbouring slices in two neighbouring stages are one 256-row image: one N = 256 batch
+                        const bool pair = q + 1 < slices && st + 1 < kBStages;
                         wait(&s_full[st], (cnt / kBStages) & 1);
-                        wait(&s_full[st + 1], (cnt / kBStages) & 1);
+                        if (pair) wait(&s_full[st + 1], (cnt / kBStages) & 1);
                         tc_fence_after();
-                        const uint32_t idesc = umma_idesc(2 * kPieceN);
+                        const uint32_t idesc = umma_idesc(pair ? 2 * kPieceN : kPieceN);
                         if (p.dbg != 3) {
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks)
@@ -202,14 +212,16 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
                                           umma_desc(aB + st * kBPieceBytes + ks * 32), idesc, (c | ks) != 0);
                         }
                         umma_commit(&s_empty[st]);
-                        umma_commit(&s_empty[st + 1]);
+                        if (pair) umma_commit(&s_empty[st + 1]);
+                        pc += pair ? 2 : 1;
+                        cnt += pair ? 2 : 1;
                     }
                     umma_commit(&s_done);  // completes after every MMA issued so far
                 }
         }
     } else {
         // ===== layer 1 + epilogues
-        const int quad = warp & 3, half = warp >> 2;  // TMEM lane quadrant (= patch of the tile), epilogue column half
+        const int quad = warp & 3, qtr = warp >> 2;   // TMEM lane quadrant (= patch of the tile), epilogue column quarter
         const int row = quad * 32 + lane;             // GEMM row of this thread's point
         const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16);
         uint32_t gi = 0;
@@ -226,14 +238,14 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int patch = tile * 4 + quad;
             const bool live = patch < p.P;
-            // ---- layer 1 on the CUDA cores (each column half = one K chunk of H1)
+            // ---- layer 1 on the CUDA cores (32 of the 128 channels per column quarter)
             float x = 0.f, y = 0.f, z = 0.f;
             if (live) {
                 const float* q = p.nbhd + (static_cast<size_t>(patch) * 32 + lane) * 3;
                 x = __ldg(q), y = __ldg(q + 1), z = __ldg(q + 2);
             }
 #pragma unroll 4
-            for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 8) {
+            for (int c0 = qtr * 32; c0 < qtr * 32 + 32; c0 += 8) {
                 __align__(16) __nv_bfloat162 h[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -248,13 +260,13 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
             a_written();
             // ---- layer 2 epilogue: f = acc + b2 -> F, patch maximum -> G (the next A operand is [F ; G])
             gemm_done();
-            for (int c0 = half * 128; c0 < half * 128 + 128 && p.dbg != 2; c0 += 16) {
+            for (int c0 = qtr * 64; c0 < qtr * 64 + 64 && p.dbg != 2; c0 += 16) {
                 float v[16];
                 tmem_ld16(trow + c0, v);
                 __align__(16) __nv_bfloat162 f2[8], g2[8];
 #pragma unroll
                 for (int e = 0; e < 16; e += 2) {
-                    const float fa = v[e] + __ldg(p.b2 + c0 + e), fb = v[e + 1] + __ldg(p.b2 + c0 + e + 1);
+                    const float fa = v[e] + s_b2[c0 + e], fb = v[e + 1] + s_b2[c0 + e + 1];
                     f2[e >> 1] = __floats2bfloat162_rn(fa, fb);
                     g2[e >> 1] = __floats2bfloat162_rn(warp_max(fa), warp_max(fb));
                 }
@@ -267,13 +279,13 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
             a_written();
             // ---- layer 3 epilogue: h2 = relu(acc + b3') -> the next A operand
             gemm_done();
-            for (int c0 = half * 256; c0 < half * 256 + 256 && p.dbg != 2; c0 += 16) {
+            for (int c0 = qtr * 128; c0 < qtr * 128 + 128 && p.dbg != 2; c0 += 16) {
                 float v[16];
                 tmem_ld16(trow + c0, v);
                 __align__(16) __nv_bfloat162 h2[8];
 #pragma unroll
                 for (int e = 0; e < 16; e += 2)
-                    h2[e >> 1] = __floats2bfloat162_rn(fmaxf(v[e] + __ldg(p.b3 + c0 + e), 0.f), fmaxf(v[e + 1] + __ldg(p.b3 + c0 + e + 1), 0.f));
+                    h2[e >> 1] = __floats2bfloat162_rn(fmaxf(v[e] + s_b3[c0 + e], 0.f), fmaxf(v[e + 1] + s_b3[c0 + e + 1], 0.f));
                 const int ch = c0 >> 6, kk = c0 & 63;
                 *reinterpret_cast<uint4*>(sA + ch * kAChunkBytes + sw128(row, kk)) = *reinterpret_cast<const uint4*>(h2);
                 *reinterpret_cast<uint4*>(sA + ch * kAChunkBytes + sw128(row, kk + 8)) = *reinterpret_cast<const uint4*>(h2 + 4);
@@ -281,14 +293,14 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(const __gri
             a_written();
             // ---- layer 4 epilogue: out = max over the points (acc) + b4
             gemm_done();
-            const int chalf = ((p.C / 16 + 1) / 2) * 16;  // columns of the first half (a multiple of 16)
-            for (int c0 = half ? chalf : 0; c0 < (half ? p.C : chalf) && p.dbg != 2; c0 += 16) {
+            const int cq = ((p.C / 16 + 3) / 4) * 16;  // columns per quarter (a multiple of 16)
+            for (int c0 = qtr * cq; c0 < min(p.C, (qtr + 1) * cq) && p.dbg != 2; c0 += 16) {
                 float v[16];
                 tmem_ld16(trow + c0, v);
                 float mine = 0.f;
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    const float m = warp_max(v[e]) + __ldg(p.b4 + c0 + e);  // the bias is constant over the points
+                    const float m = warp_max(v[e]) + s_b4[c0 + e];  // the bias is constant over the points
                     if (lane == e) mine = m;
                 }
                 if (live && lane < 16) p.out[static_cast<size_t>(patch) * p.C + c0 + lane] = mine;

@@ -21,11 +21,11 @@ def _fold(w: torch.Tensor, b: torch.Tensor, bn_w, bn_b, mean, var, eps: float):
 
 def tile_weight(w: torch.Tensor) -> torch.Tensor:
     """(N, K) -> the pre-tiled BF16 layout gm3d_encoder_fwd_bf16 streams: for K chunk c (64 wide) and output slice
-    q (128 rows; N zero-padded to a multiple of 256), piece c * slices + q is the 16 KB K-major SWIZZLE_128B shared-memory image
+    q (128 rows, zero-padded), piece c * slices + q is the 16 KB K-major SWIZZLE_128B shared-memory image
     (16-byte group j of row r sits at group j ^ (r % 8))."""
     n, k = w.shape
     assert k % 64 == 0
-    slices = 2 * ((n + 255) // 256)  # pairs of 128-row slices: the kernel issues N = 256 tensor-core batches
+    slices = (n + 127) // 128
     wp = torch.zeros((slices * 128, k), dtype=torch.bfloat16, device=w.device)
     wp[:n] = w.to(torch.bfloat16)
     t = wp.view(slices, 128, k // 64, 8, 8).permute(2, 0, 1, 3, 4).contiguous()   # (c, q, r, j, e)

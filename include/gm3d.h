@@ -229,9 +229,9 @@ int gm3d_gather_points_f32(const float* xyz, const int32_t* idx, const int64_t* 
  * the caller: w1 (128,3) f32, b1 (128); w2 (256,128) bf16, b2 (256); w3 (512,512) bf16 with its input columns
  * ordered [per-point feature (256) ; patch maximum (256)], b3 (512); w4 (C,512) bf16, b4 (C).
  * The three bf16 matrices are passed PRE-TILED (gm3d_b200/encoder.py: tile_weight): for K chunk c (64 input
- * channels) and output slice q (128 channels; N zero-padded to a multiple of 256), piece (c, q) is the 16 KB K-major SWIZZLE_128B
+ * channels) and output slice q (128 channels, zero-padded), piece (c, q) is the 16 KB K-major SWIZZLE_128B
  * shared-memory image -- element (row r, k) at byte r*128 + ((k/8 ^ r%8) * 16) + (k%8)*2 -- stored at piece index
- * c * (2 * ceil(N/256)) + q, so that one bulk copy per piece feeds the tensor cores.  Pointers 16-byte aligned.  *status (device int32 or NULL) is set to 1 if a tensor-core batch never completed.
+ * c * ceil(N/128) + q, so that one bulk copy per piece feeds the tensor cores.  Pointers 16-byte aligned.  *status (device int32 or NULL) is set to 1 if a tensor-core batch never completed.
  * n_points must be 32 (one warp per patch), else GM3D_ENOSUP. */
 int gm3d_encoder_fwd_bf16(const float* nbhd, int P, int n_points, const float* w1, const float* b1, const void* w2,
                           const float* b2, const void* w3, const float* b3, const void* w4, const float* b4, int C,
