@@ -12,7 +12,7 @@
 //                and -- if patch g is masked -- run Chamfer forward + backward of that patch against the
 //                prediction (chamfer_patch.cuh) while the target patch is still in registers.
 //                One worker first computes the cloud's hard-patch mask (mask_select.cuh).
-//   Sampler warps turn into workers when the last centre is out.  The last CTA to finish reduces the
+//   Sampler warps turn into workers when the last centre is out (patches are handed out by a shared counter).  The last CTA to finish reduces the
 //   per-patch losses to the scalar loss + statistics vector (ticket in the workspace).
 //
 // FPS is a chain of G dependent rounds and cannot be made shorter than its latency; everything else
@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 12 ? 2 : 1) cloud_step_ke
     __shared__ int2 s_red[2][kCsMaxFpsWarps];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_mask_ready;  // 1 once s_msel / s_mrank are valid
+    __shared__ int s_next;        // next patch id to hand out (patches are claimed in the order their centres appear)
 
     // Programmatic dependent launch: the caller promised that the next kernel in the stream touches none of
     // this launch's buffers, so it may start filling SMs as soon as every CTA of this grid is resident.
@@ -134,16 +135,13 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 12 ? 2 : 1) cloud_step_ke
     short* s_mrank = reinterpret_cast<short*>(smem_raw + L.mrank);
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // Roles: sampler warps 0..FW-1 (one per SM sub-partition when FW = 4), the rest are workers; the last worker
-    // first computes the cloud's mask.  (Measured alternatives, both slower: all sampler warps on ONE
+    // Roles: sampler warps 0..FW-1 (one per SM sub-partition when FW = 4), the rest are workers from the start
+    // (the samplers join them after the last round); the last worker first computes the cloud's mask.  (Measured alternatives, both slower: all sampler warps on ONE
     // sub-partition with no worker next to them -- the chain then queues behind itself; and a single sampler
     // warp with 32 points per lane -- 670 cycles per round.  Sharing sub-partitions costs the chain about 2x
     // its stand-alone latency, but the workers' issue slots are what bounds the CTA.)
     const bool is_fps = warp < FW;
     const int ftid = tid;  // sampler thread index
-    const bool is_worker = warp >= FW;
-    const int nworkers = WARPS - FW;
-    const int wi = warp - FW;
     const bool is_mask_warp = LOSS && warp == WARPS - 1;
     const float* cloud = p.xyz + static_cast<size_t>(b) * N * 3;
     const int M = G - p.len_keep;
@@ -160,7 +158,10 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 12 ? 2 : 1) cloud_step_ke
         s_sel[g] = 0;  // FPS starts at point 0
         mbar_init(&s_ready[g], 1);
     }
-    if (tid == 0) s_mask_ready = 0;
+    if (tid == 0) {
+        s_mask_ready = 0;
+        if constexpr (WARPS <= 12) s_next = 0;
+    }
     mbar_fence_init();
     __syncthreads();
     if (tid == 0) mbar_arrive(&s_ready[0]);  // centre 0 is point 0: known from the start
@@ -275,60 +276,73 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 12 ? 2 : 1) cloud_step_ke
         if (lane == 0) st_volatile_s32(&s_mask_ready, 1);
     }
 
-    // ---------------- workers: patch g = worker, worker + #workers, ... (centres appear in that order)
-    if (is_worker) {
-        u64* cb = reinterpret_cast<u64*>(smem_raw + L.cand) + warp * 64;
-        ChamferWarpScratch* csc = LOSS ? reinterpret_cast<ChamferWarpScratch*>(smem_raw + L.cham) + warp : nullptr;
-        const int nf = 3 * k;  // floats per patch
-        for (int g = wi; g < G; g += nworkers) {
-            if (p.dbg_mode == 1 || p.dbg_mode == 3) break;
-            const long long w0 = tr ? clock64() : 0;
-            mbar_wait(&s_ready[g], 0);  // suspended in hardware until centre g is published: no polling instructions
-            const int c = s_sel[g];
-            if (tr && lane == 0) tr[32 + warp] += clock64() - w0;
-            const float qx = sx[c], qy = sy[c], qz = sz[c];
-            u64 top;
-            float thr;
-            if (!bootstrap_query(sx, sy, sz, 0, qx, qy, qz, k, lane, cb, top, thr))  // tiny cloud / heavy ties
-                top = knn_stream_points(kKeyInf, __uint_as_float(kFltMaxBits), sx, sy, sz, 0, N, qx, qy, qz, k, lane, cb);
-            else if (N > kKnnTile)
-                top = knn_stream_points(top, thr, sx + kKnnTile, sy + kKnnTile, sz + kKnnTile, kKnnTile, N - kKnnTile, qx,
-                                        qy, qz, k, lane, cb);
+    // ---------------- workers.  Two CTAs per SM (12 warps): patches are handed out by a shared counter and the sampler
+    // warps join in once the last centre is out (measured 20.3 -> 19.3 us per step).  One CTA per SM (24 warps): the
+    // samplers finish late anyway and a fixed round-robin measured faster.
+    constexpr bool DYNAMIC = WARPS <= 12;
+    u64* cb = reinterpret_cast<u64*>(smem_raw + L.cand) + warp * 64;
+    ChamferWarpScratch* csc = LOSS ? reinterpret_cast<ChamferWarpScratch*>(smem_raw + L.cham) + warp : nullptr;
+    const int nf = 3 * k;  // floats per patch
+    auto process_patch = [&](const int g) {
+        const long long w0 = tr ? clock64() : 0;
+        mbar_wait(&s_ready[g], 0);  // suspended in hardware until centre g is published: no polling instructions
+        const int c = s_sel[g];
+        if (tr && lane == 0) tr[32 + warp] += clock64() - w0;
+        const float qx = sx[c], qy = sy[c], qz = sz[c];
+        u64 top;
+        float thr;
+        if (!bootstrap_query(sx, sy, sz, 0, qx, qy, qz, k, lane, cb, top, thr))  // tiny cloud / heavy ties
+            top = knn_stream_points(kKeyInf, __uint_as_float(kFltMaxBits), sx, sy, sz, 0, N, qx, qy, qz, k, lane, cb);
+        else if (N > kKnnTile)
+            top = knn_stream_points(top, thr, sx + kKnnTile, sy + kKnnTile, sz + kKnnTile, kKnnTile, N - kKnnTile, qx,
+                                    qy, qz, k, lane, cb);
 
-            // gather + centre-normalise; lane l < k owns neighbour l
-            const unsigned pi = lane < k ? static_cast<unsigned>(top & 0xffffffffu) : 0u;
-            const float ox = sx[pi], oy = sy[pi], oz = sz[pi];
-            const float bx = __fsub_rn(ox, qx), by = __fsub_rn(oy, qy), bz = __fsub_rn(oz, qz);
-            const size_t row = (static_cast<size_t>(b) * G + g) * k;
-            if (lane < k) {
-                if (p.knn_idx) p.knn_idx[row + lane] = static_cast<int64_t>(pi);
-                if (p.nbhd_org) {
-                    float* o = p.nbhd_org + (row + lane) * 3;
-                    o[0] = ox, o[1] = oy, o[2] = oz;
-                }
-                float* o = p.nbhd + (row + lane) * 3;
-                o[0] = bx, o[1] = by, o[2] = bz;
+        // gather + centre-normalise; lane l < k owns neighbour l
+        const unsigned pi = lane < k ? static_cast<unsigned>(top & 0xffffffffu) : 0u;
+        const float ox = sx[pi], oy = sy[pi], oz = sz[pi];
+        const float bx = __fsub_rn(ox, qx), by = __fsub_rn(oy, qy), bz = __fsub_rn(oz, qz);
+        const size_t row = (static_cast<size_t>(b) * G + g) * k;
+        if (lane < k) {
+            if (p.knn_idx) p.knn_idx[row + lane] = static_cast<int64_t>(pi);
+            if (p.nbhd_org) {
+                float* o = p.nbhd_org + (row + lane) * 3;
+                o[0] = ox, o[1] = oy, o[2] = oz;
             }
-            if (LOSS && p.dbg_mode != 2) {
-                while (ld_volatile_s32(&s_mask_ready) == 0) __nanosleep(64);
-                const int mr = s_mrank[g];
-                if (mr >= 0) {  // warp-uniform: patch g is masked, its prediction is row b*M + mr
-                    const size_t pp = static_cast<size_t>(b) * M + mr;
-                    const size_t pe = pp * k + lane;  // element (patch, lane) of the (P, k) outputs
-                    const float* pa = p.pred + pp * nf + 3 * (lane < k ? lane : 0);
-                    const float ax = __ldg(pa), ay = __ldg(pa + 1), az = __ldg(pa + 2);
-                    const ChamferWarpOut o = chamfer_patch_warp(ax, ay, az, bx, by, bz, k, p.norm, p.gscale1, p.gscale2, lane, csc);
-                    if (lane < k) {
-                        if (p.dist1) p.dist1[pe] = o.dist1;
-                        if (p.dist2) p.dist2[pe] = o.dist2;
-                        if (p.idx1) p.idx1[pe] = o.idx1;
-                        if (p.idx2) p.idx2[pe] = o.idx2;
-                        float* go = p.gxyz1 + pe * 3;
-                        go[0] = o.gx, go[1] = o.gy, go[2] = o.gz;
-                    }
-                    if (lane == 0 && p.per_patch) p.per_patch[pp] = o.per_patch;
+            float* o = p.nbhd + (row + lane) * 3;
+            o[0] = bx, o[1] = by, o[2] = bz;
+        }
+        if (LOSS && p.dbg_mode != 2) {
+            while (ld_volatile_s32(&s_mask_ready) == 0) __nanosleep(64);
+            const int mr = s_mrank[g];
+            if (mr >= 0) {  // warp-uniform: patch g is masked, its prediction is row b*M + mr
+                const size_t pp = static_cast<size_t>(b) * M + mr;
+                const size_t pe = pp * k + lane;  // element (patch, lane) of the (P, k) outputs
+                const float* pa = p.pred + pp * nf + 3 * (lane < k ? lane : 0);
+                const float ax = __ldg(pa), ay = __ldg(pa + 1), az = __ldg(pa + 2);
+                const ChamferWarpOut o = chamfer_patch_warp(ax, ay, az, bx, by, bz, k, p.norm, p.gscale1, p.gscale2, lane, csc);
+                if (lane < k) {
+                    if (p.dist1) p.dist1[pe] = o.dist1;
+                    if (p.dist2) p.dist2[pe] = o.dist2;
+                    if (p.idx1) p.idx1[pe] = o.idx1;
+                    if (p.idx2) p.idx2[pe] = o.idx2;
+                    float* go = p.gxyz1 + pe * 3;
+                    go[0] = o.gx, go[1] = o.gy, go[2] = o.gz;
                 }
+                if (lane == 0 && p.per_patch) p.per_patch[pp] = o.per_patch;
             }
+        }
+    };
+    if (p.dbg_mode != 1 && p.dbg_mode != 3) {
+        if constexpr (DYNAMIC) {
+            for (;;) {
+                int g = 0;
+                if (lane == 0) g = atomicAdd(&s_next, 1);
+                g = __shfl_sync(kFull, g, 0);
+                if (g >= G) break;
+                process_patch(g);
+            }
+        } else if (warp >= FW) {
+            for (int g = warp - FW; g < G; g += WARPS - FW) process_patch(g);
         }
     }
 
