@@ -217,8 +217,12 @@ class HostStagedStep(GroupLossStep):
     scalars), `h_per_patch` (the (B,M) loss matrix the loss predictor is trained on) and `h_mask`.  One H2D
     copy, the step, one D2H copy -- all three part of the captured graph."""
 
-    def __init__(self, *a, **kw):
+    def __init__(self, *a, cloud_only: bool = False, **kw):
+        """cloud_only: only the point clouds cross PCIe each step; `pred` and `loss_pred` stay where the reference
+        produces them -- on the device, as decoder / loss-predictor outputs
+        (engine_pretrain_Classifier_SVM.py:108-118,157-164)."""
         super().__init__(*a, **kw)
+        self.cloud_only = cloud_only
         self.h_in = torch.empty(self.in_arena.shape, dtype=torch.uint8, pin_memory=True)
         self.h_res = torch.empty(self.res_arena.shape, dtype=torch.uint8, pin_memory=True)
         self.h_xyz, self.h_pred, self.h_loss_pred = self._carve(self.h_in, self._in_specs)
@@ -226,14 +230,17 @@ class HostStagedStep(GroupLossStep):
 
     @property
     def h2d_bytes(self) -> int:
-        return self.h_in.numel()
+        return self.xyz.numel() * 4 if self.cloud_only else self.h_in.numel()
 
     @property
     def d2h_bytes(self) -> int:
         return self.h_res.numel()
 
     def enqueue(self, flags: int = 0) -> None:
-        self.in_arena.copy_(self.h_in, non_blocking=True)
+        if self.cloud_only:
+            self.xyz.copy_(self.h_xyz, non_blocking=True)
+        else:
+            self.in_arena.copy_(self.h_in, non_blocking=True)
         super().enqueue(flags)
         self.h_res.copy_(self.res_arena, non_blocking=True)
 
