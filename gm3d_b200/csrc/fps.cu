@@ -1,6 +1,7 @@
 // Farthest-point sampling for sm_100a: one CTA per cloud, the cloud and its running-min array held in
-// REGISTERS (PPT points per thread), the cloud additionally staged once in shared memory (1-D bulk copy
-// through the TMA engine) so the winner's coordinates are a broadcast LDS.  One __syncthreads per round:
+// REGISTERS (PPT points per thread as packed FP32x2 pairs: FADD2 / FMUL2 / FFMA2 distance updates), the cloud
+// additionally staged once in shared memory (1-D bulk copy through the TMA engine) so the winner's
+// coordinates are a broadcast LDS.  One __syncthreads per round: thread arg-max by a pairwise tournament,
 // warp arg-max with two REDUX instructions (max of the order-preserving int view of the distance, then
 // min of the candidate indices), per-warp results double-buffered in shared memory, and every warp
 // re-reduces the <=32 warp results redundantly so no second barrier / broadcast is needed.
@@ -8,6 +9,7 @@
 // Replaces pointnet2_utils.furthest_point_sample (+ gather_operation for the centres):
 // /root/reference/Point-MAE_SA3D/utils/miscc.py:13-20, ..._feature_besed.py:1229-1236.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -47,40 +49,51 @@ __global__ void __launch_bounds__(THREADS, 1)
         __syncthreads();
     }
 
-    float px[PPT], py[PPT], pz[PPT], pt[PPT];
+    // point pairs in packed FP32x2 registers (slots 2h, 2h+1 <-> points (2h) * THREADS + tid, (2h+1) * THREADS + tid)
+    float2 X[PPT / 2], Y[PPT / 2], Z[PPT / 2], T[PPT / 2];
 #pragma unroll
     for (int s = 0; s < PPT; ++s) {
         const int k = s * THREADS + tid;
+        float x = 0.0f, y = 0.0f, z = 0.0f, t = -1.0f;  // min(d, -1) stays -1: never selected (ties resolve to a lower, real index)
         if (k < N) {
-            px[s] = s_xyz[3 * k + 0];
-            py[s] = s_xyz[3 * k + 1];
-            pz[s] = s_xyz[3 * k + 2];
-            const float mag = sumsq_nvcc(px[s], py[s], pz[s]);
+            x = s_xyz[3 * k + 0], y = s_xyz[3 * k + 1], z = s_xyz[3 * k + 2];
             // upstream: `if (mag <= 1e-3) continue;` with a double literal => double compare
-            pt[s] = (static_cast<double>(mag) <= 1e-3) ? -1.0f : 1e10f;
-        } else {
-            px[s] = py[s] = pz[s] = 0.0f;
-            pt[s] = -1.0f;  // min(d, -1) stays -1: never selected (ties resolve to a lower, real index)
+            t = (static_cast<double>(sumsq_nvcc(x, y, z)) <= 1e-3) ? -1.0f : 1e10f;
         }
+        if (s & 1) X[s >> 1].y = x, Y[s >> 1].y = y, Z[s >> 1].y = z, T[s >> 1].y = t;
+        else X[s >> 1].x = x, Y[s >> 1].x = y, Z[s >> 1].x = z, T[s >> 1].x = t;
     }
 
     int old = 0;
     if (tid == 0) s_sel[0] = 0;
+    const int2* red_rd = &s_red[0][lane < NWARPS ? lane : 0];  // duplicates of warp 0's entry are harmless
     for (int j = 1; j < G; ++j) {
-        const float x1 = s_xyz[3 * old + 0], y1 = s_xyz[3 * old + 1], z1 = s_xyz[3 * old + 2];
-        float best = -1.0f;
-        int besti = 0;
+        const float* w = s_xyz + 3 * old;
+        const float x1 = w[0], y1 = w[1], z1 = w[2];
+        const float2 x2 = make_float2(x1, x1), y2 = make_float2(y1, y1), z2 = make_float2(z1, z1);
+        float m[PPT];
 #pragma unroll
-        for (int s = 0; s < PPT; ++s) {
-            const float d = sumsq_nvcc(px[s] - x1, py[s] - y1, pz[s] - z1);
-            const float d2 = fminf(d, pt[s]);
-            pt[s] = d2;
-            if (d2 > best) {  // strict: the lower k (= lower s) keeps a tie inside a thread
-                best = d2;
-                besti = s * THREADS + tid;
+        for (int h = 0; h < PPT / 2; ++h) {
+            const float2 d = sumsq_nvcc2(sub2(X[h], x2), sub2(Y[h], y2), sub2(Z[h], z2));
+            T[h].x = fminf(d.x, T[h].x);
+            T[h].y = fminf(d.y, T[h].y);
+            m[2 * h] = T[h].x, m[2 * h + 1] = T[h].y;
+        }
+        // thread arg-max, lowest slot (= lowest point index of the thread) on ties: pairwise tournament
+        int mi[PPT];
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) mi[s] = s;
+#pragma unroll
+        for (int ww = 1; ww < PPT; ww <<= 1) {
+#pragma unroll
+            for (int s = 0; s < PPT; s += 2 * ww) {
+                const bool hi = m[s + ww] > m[s];
+                m[s] = hi ? m[s + ww] : m[s];
+                mi[s] = hi ? mi[s + ww] : mi[s];
             }
         }
-        const int v = f2ord(best);
+        const int v = f2ord(m[0]);
+        const int besti = mi[0] * THREADS + tid;
         const int vmax = __reduce_max_sync(kFull, v);
         const int kmin = __reduce_min_sync(kFull, v == vmax ? besti : INT_MAX);
         if (NWARPS == 1) {
@@ -88,7 +101,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         } else {
             if (lane == 0) s_red[j & 1][warp] = make_int2(vmax, kmin);
             __syncthreads();
-            const int2 r = lane < NWARPS ? s_red[j & 1][lane] : make_int2(INT_MIN, INT_MAX);
+            const int2 r = red_rd[(j & 1) * 32];
             const int gmax = __reduce_max_sync(kFull, r.x);
             old = __reduce_min_sync(kFull, r.x == gmax ? r.y : INT_MAX);
         }
@@ -191,11 +204,13 @@ GM3D_API int gm3d_fps_f32(const float* xyz, int B, int N, int G, int32_t* idx, f
         return launch_status();
     }
     if (static_cast<size_t>((N + 3) & ~3) * 12 + static_cast<size_t>(G) * 4 > 200 * 1024) return GM3D_ENOSUP;
+    // few warps with 8 points per thread: one warp per SM sub-partition is the shortest chain per round
+    static const int variant = getenv("GM3D_FPS_VARIANT") ? atoi(getenv("GM3D_FPS_VARIANT")) : 0;  // tuning aid
     if (N <= 128) return launch_fps_reg<64, 2>(xyz, B, N, G, idx, centers, st);
-    if (N <= 256) return launch_fps_reg<128, 2>(xyz, B, N, G, idx, centers, st);
+    if (N <= 256) return launch_fps_reg<64, 4>(xyz, B, N, G, idx, centers, st);
     if (N <= 512) return launch_fps_reg<128, 4>(xyz, B, N, G, idx, centers, st);
-    if (N <= 1024) return launch_fps_reg<256, 4>(xyz, B, N, G, idx, centers, st);
-    if (N <= 2048) return launch_fps_reg<512, 4>(xyz, B, N, G, idx, centers, st);
+    if (N <= 1024) return variant == 1 ? launch_fps_reg<256, 4>(xyz, B, N, G, idx, centers, st) : launch_fps_reg<128, 8>(xyz, B, N, G, idx, centers, st);
+    if (N <= 2048) return variant == 1 ? launch_fps_reg<512, 4>(xyz, B, N, G, idx, centers, st) : launch_fps_reg<256, 8>(xyz, B, N, G, idx, centers, st);
     if (N <= 4096) return launch_fps_reg<512, 8>(xyz, B, N, G, idx, centers, st);
-    return launch_fps_reg<1024, 8>(xyz, B, N, G, idx, centers, st);
+    return variant == 1 ? launch_fps_reg<1024, 8>(xyz, B, N, G, idx, centers, st) : launch_fps_reg<512, 16>(xyz, B, N, G, idx, centers, st);
 }
