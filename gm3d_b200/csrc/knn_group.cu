@@ -8,6 +8,9 @@
 //
 // Replaces knn_cuda.KNN(k, transpose_mode=True).forward and the index arithmetic / gather / subtract of
 // Group.forward: /root/reference/Point-MAE_SA3D/models/Point_MAE.py:57-78, ..._feature_besed.py:1238-1260.
+#include <stdlib.h>
+
+#include "knn_large.cuh"
 #include "knn_select.cuh"
 
 namespace gm3d {
@@ -147,6 +150,12 @@ static int launch_knn_q(dim3 grid, cudaStream_t st, const float* ref, const floa
 
 static int launch_knn_group(const float* ref, const float* query, int B, int N, int G, int k, float* dist,
                             int64_t* idx, float* nbhd, float* nbhd_org, cudaStream_t st) {
+    // 1024 < N <= 16384: the two-phase kernel (knn_large.cuh); GM3D_KNN_LARGE=0 keeps the streaming kernel (A/B runs)
+    static const bool large_ok = [] { const char* e = getenv("GM3D_KNN_LARGE"); return !(e && e[0] == '0'); }();
+    if (large_ok && N > kKlChunk && N <= kKlMaxN) {
+        const int rc = launch_knn_large(ref, query, B, N, G, k, dist, idx, nbhd, nbhd_org, st);
+        if (rc != GM3D_ENOSUP) return rc;
+    }
     if (B > 65535) return GM3D_ENOSUP;
     const int use_bulk = (N % 4 == 0) && (reinterpret_cast<uintptr_t>(ref) % 16 == 0);
     // queries per warp: share each streamed tile between more queries when the cloud is large, but keep

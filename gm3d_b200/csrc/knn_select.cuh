@@ -153,6 +153,58 @@ static __device__ __noinline__ u64 order_two_exact(u64 c0, u64 c1, bool two, int
     return top;
 }
 
+// Exact ordering of `total` (<= 64) candidate points whose tile-local indices are compacted in the first 128
+// bytes of cb (unsigned short each; written by the calling warp, not yet fenced): `top` receives the k nearest as
+// ascending keys (lanes >= k hold larger keys or the sentinel), `thr` the k-th distance.  The candidate set must
+// contain every point within the k-th distance (any superset works).  base: global index of the tile's first point.
+__device__ __forceinline__ void order_candidates(const float* __restrict__ sx, const float* __restrict__ sy,
+                                                 const float* __restrict__ sz, int base, int total, float2 q2x, float2 q2y,
+                                                 float2 q2z, int k, int lane, u64* __restrict__ cb, u64& top, float& thr) {
+    unsigned short* cl = reinterpret_cast<unsigned short*>(cb);
+    __syncwarp();
+    // ---- every lane re-evaluates up to two candidates (same expression => same bits as in the scan), the
+    // distances alone are sorted, and each candidate finds its rank by binary search
+    const int i0 = lane < total ? cl[lane] : 0, i1 = 32 + lane < total ? cl[32 + lane] : 0;
+    const float2 dd = sumsq_acc2(sub2(make_float2(sx[i0], sx[i1]), q2x), sub2(make_float2(sy[i0], sy[i1]), q2y),
+                                 sub2(make_float2(sz[i0], sz[i1]), q2z));
+    const unsigned d0 = lane < total ? __float_as_uint(dd.x) : kInfBits;
+    const unsigned d1 = 32 + lane < total ? __float_as_uint(dd.y) : kInfBits;
+    const u64 c0 = lane < total ? make_key_bits(d0, static_cast<unsigned>(base + i0)) : kKeyInf;
+    const u64 c1 = 32 + lane < total ? make_key_bits(d1, static_cast<unsigned>(base + i1)) : kKeyInf;
+    unsigned srt = sort_u32<32>(d0, lane);
+    const int extra = total - 32;  // warp-uniform
+    if (extra > 0) {
+        unsigned e = d1 | (32 + lane < total ? 0u : 0xffffffffu);  // lanes without a second candidate: all ones
+        if (extra <= 8) e = sort_u32<8>(e, lane);
+        else if (extra <= 16) e = sort_u32<16>(e, lane);
+        else e = sort_u32<32>(e, lane);
+        const unsigned er = __shfl_sync(kFull, e, 31 - lane);
+        srt = merge_u32(min(srt, er), lane);
+    }
+    const unsigned thrb = __shfl_sync(kFull, srt, k - 1);
+    const unsigned nxt = __shfl_down_sync(kFull, srt, 1);
+    const bool tie = (lane + 1 < k) && (srt == nxt);
+    const int cnt = __popc(__ballot_sync(kFull, d0 <= thrb)) + __popc(__ballot_sync(kFull, d1 <= thrb));
+    if (__any_sync(kFull, tie) || cnt != k) {  // bit-equal distances among the best k+1: exact 64-bit ordering
+        top = order_two_exact(c0, c1, extra > 0, lane);
+        thr = key_dist(__shfl_sync(kFull, top, k - 1));
+        __syncwarp();
+        return;
+    }
+    unsigned* so = reinterpret_cast<unsigned*>(cb);  // every lane holds its keys in registers now
+    __syncwarp();
+    const int r0 = rank_in_sorted(srt, d0);
+    if (d0 <= thrb) so[r0] = static_cast<unsigned>(c0);
+    if (extra > 0) {
+        const int r1 = rank_in_sorted(srt, d1);
+        if (d1 <= thrb) so[r1] = static_cast<unsigned>(c1);
+    }
+    __syncwarp();
+    top = lane < k ? make_key_bits(srt, so[lane]) : kKeyInf;
+    thr = __uint_as_float(thrb);
+    __syncwarp();
+}
+
 // Bootstrap one query on a full SoA tile.  On success `top` holds the tile's k nearest (ascending keys, lanes
 // >= k hold larger keys or the sentinel) and `thr` the k-th distance.  Returns false when more than 64
 // points pass the bound (heavy ties / tiny tiles): the caller then streams the tile instead.
@@ -227,48 +279,7 @@ __device__ __forceinline__ bool bootstrap_query(const float* __restrict__ sx, co
         off += pm != 0;
         pm &= pm - 1;
     }
-    __syncwarp();
-    // ---- every lane re-evaluates up to two candidates (same expression => same bits as in the scan), the
-    // distances alone are sorted, and each candidate finds its rank by binary search
-    const int i0 = lane < total ? cl[lane] : 0, i1 = 32 + lane < total ? cl[32 + lane] : 0;
-    const float2 dd = sumsq_acc2(sub2(make_float2(sx[i0], sx[i1]), q2x), sub2(make_float2(sy[i0], sy[i1]), q2y),
-                                 sub2(make_float2(sz[i0], sz[i1]), q2z));
-    const unsigned d0 = lane < total ? __float_as_uint(dd.x) : kInfBits;
-    const unsigned d1 = 32 + lane < total ? __float_as_uint(dd.y) : kInfBits;
-    const u64 c0 = lane < total ? make_key_bits(d0, static_cast<unsigned>(base + i0)) : kKeyInf;
-    const u64 c1 = 32 + lane < total ? make_key_bits(d1, static_cast<unsigned>(base + i1)) : kKeyInf;
-    unsigned srt = sort_u32<32>(d0, lane);
-    const int extra = total - 32;  // warp-uniform
-    if (extra > 0) {
-        unsigned e = d1 | (32 + lane < total ? 0u : 0xffffffffu);  // lanes without a second candidate: all ones
-        if (extra <= 8) e = sort_u32<8>(e, lane);
-        else if (extra <= 16) e = sort_u32<16>(e, lane);
-        else e = sort_u32<32>(e, lane);
-        const unsigned er = __shfl_sync(kFull, e, 31 - lane);
-        srt = merge_u32(min(srt, er), lane);
-    }
-    const unsigned thrb = __shfl_sync(kFull, srt, k - 1);
-    const unsigned nxt = __shfl_down_sync(kFull, srt, 1);
-    const bool tie = (lane + 1 < k) && (srt == nxt);
-    const int cnt = __popc(__ballot_sync(kFull, d0 <= thrb)) + __popc(__ballot_sync(kFull, d1 <= thrb));
-    if (__any_sync(kFull, tie) || cnt != k) {  // bit-equal distances among the best k+1: exact 64-bit ordering
-        top = order_two_exact(c0, c1, extra > 0, lane);
-        thr = key_dist(__shfl_sync(kFull, top, k - 1));
-        __syncwarp();
-        return true;
-    }
-    unsigned* so = reinterpret_cast<unsigned*>(cb);  // every lane holds its keys in registers now
-    __syncwarp();
-    const int r0 = rank_in_sorted(srt, d0);
-    if (d0 <= thrb) so[r0] = static_cast<unsigned>(c0);
-    if (extra > 0) {
-        const int r1 = rank_in_sorted(srt, d1);
-        if (d1 <= thrb) so[r1] = static_cast<unsigned>(c1);
-    }
-    __syncwarp();
-    top = lane < k ? make_key_bits(srt, so[lane]) : kKeyInf;
-    thr = __uint_as_float(thrb);
-    __syncwarp();
+    order_candidates(sx, sy, sz, base, total, q2x, q2y, q2z, k, lane, cb, top, thr);
     return true;
 }
 

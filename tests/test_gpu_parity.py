@@ -137,6 +137,43 @@ def test_knn_all_ties_and_transpose_mode(cuda):
         KNN(33, True)(dev(xyz, cuda), dev(qq, cuda))
 
 
+@pytest.mark.parametrize("B,N,G,k", [
+    (2, 1025, 33, 32), (1, 2047, 9, 7), (3, 5000, 70, 32), (1, 6145, 64, 16), (2, 8192, 77, 1), (1, 12000, 40, 32),
+    (1, 16384, 50, 32), (1, 20000, 24, 32), (40, 2048, 128, 32),
+])
+def test_knn_large_two_phase_edges(cuda, B, N, G, k):
+    """1024 < N <= 16384 runs the two-phase kernel (knn_large.cuh): ragged last chunk, 2..16 chunks (warp roles
+    differ for <= 8 and > 8 chunks), query blocks that do not divide G, and N just past its range (streaming kernel)."""
+    from gm3d_b200.knn import KNN
+    xyz = synthetic_clouds(B, N, 900 + N + k, "sphere")
+    rng = np.random.default_rng(N + G)
+    q = np.stack([xyz[b, rng.choice(N, G, replace=False)] for b in range(B)])
+    q[:, ::3] += rng.standard_normal((B, q[:, ::3].shape[1], 3)).astype(np.float32) * 0.05  # off-cloud queries too
+    D, I = KNN(k, transpose_mode=True)(dev(xyz, cuda), dev(q, cuda))
+    Dw, Iw = co.knn(xyz, q, k)
+    assert np.array_equal(host(I), Iw)
+    assert np.array_equal(host(D).view(np.uint32), Dw.view(np.uint32))
+
+
+def test_knn_large_heavy_ties(cuda):
+    """More than 64 points within the bound (duplicates, lattice distances): the exact streaming fallback inside the
+    two-phase kernel, and bit-equal distances among the best k+1 (64-bit key ordering)."""
+    from gm3d_b200.knn import KNN
+    rng = np.random.default_rng(5)
+    N = 4096
+    ref = np.zeros((3, N, 3), dtype=np.float32)
+    ref[1] = rng.integers(0, 6, size=(N, 3)).astype(np.float32)            # lattice: many equal distances
+    base = synthetic_clouds(1, 64, 3, "ball")[0]
+    ref[2] = base[rng.integers(0, 64, size=N)]                              # 64 distinct points, 64 copies each
+    q = np.stack([np.ones((5, 3), np.float32), ref[1, :5] + 0.5, ref[2, :5]])
+    for k in (32, 9):
+        D, I = KNN(k, True)(dev(ref, cuda), dev(q, cuda))
+        Dw, Iw = co.knn(ref, q, k)
+        assert np.array_equal(host(I), Iw)
+        assert np.array_equal(host(D).view(np.uint32), Dw.view(np.uint32))
+    assert (host(I)[0] == np.arange(9)[None]).all()
+
+
 # ------------------------------------------------------------------------------------------ Group
 @pytest.mark.parametrize("tag", ["c1", "m2ae_l2", "ragged", "g_eq_n"])
 def test_group_matches_reference_golden(cuda, golden, tag):
