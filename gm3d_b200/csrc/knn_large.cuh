@@ -1,27 +1,38 @@
 // Exact kNN + patch gather for clouds of 1024 < N <= 8192 points: two-phase selection, sm_100a.
 //
 // The streaming filter of knn_select.cuh tightens its bound only as fast as the stream reveals near points
-// (k ln(N/1024) late passes per query, each one a divergent append).  Here the bound is known before any
-// candidate is collected:
+// (k ln(N/1024) late passes per query, each one a divergent append), and every (query, point) pair costs the six
+// FP32 operations of the reference distance expression.  Here a CHEAP SCREEN decides which points can matter, and
+// only those are evaluated with the reference expression:
 //
-//   phase 1  the cloud sits in shared memory chunk by chunk ([x 1024 | y 1024 | z 1024] per chunk of 1024
-//            points, natural order).  A warp owns one chunk: lane L holds the chunk's points
-//            32m + ((L + m) & 31), m = 0..31, in registers (conflict-free scalar LDS, skewed ownership) and
-//            evaluates them against a block of queries with packed FP32x2 math.  All that is kept per (query,
-//            chunk, lane) are the MINIMA of its four 8-point groups (m = 8s..8s+7; 3-input FMNMX), truncated to
-//            their upper 16 bits and stored as one 8-byte word.  No compare, no branch, no shuffle.
-//   phase 2  a warp owns one query.  Its nchunks * 128 group minima are read as packed 16-bit pairs: the packed
-//            minimum over a lane's words gives two minima of disjoint point sets per lane, 64 in all, whose k-th
-//            smallest T bounds the k-th distance (the packed 16-bit sort of knn_select.cuh).  Only groups whose
-//            minimum is <= T can hold a candidate -- about k of them; they are compacted into a list, and the
-//            warp re-evaluates FOUR listed groups per step (8 lanes each; the skewed ownership keeps the reads
-//            spread over the banks), appending `d <= T` by ballot.  The <= 64 candidates are ordered exactly by
-//            order_candidates().  Anything unusual (more than 64 candidates, more than 128 groups: heavy ties)
-//            takes the exact streaming selection instead.
+//   screen   t(p, q) = |p|^2 - 2 p.q = |p - q|^2 - |q|^2 as three chained FMAs on the precomputed |p|^2 (half the
+//            FP32-pipe work of the reference expression).  |t_fp + |q|^2 - d_fp| <= E(q) for every point, where
+//            d_fp is the reference FP32 distance and E = 24 * 2^-24 * (max|p| + |q|)^2 (derivation below); every
+//            decision taken on t keeps a margin of E, so the screen can only ADD candidates, never lose one.
+//   phase 1  the cloud sits in shared memory chunk by chunk ([x | y | z | |p|^2] x 1024 per chunk of 1024 points,
+//            natural order).  A warp owns a quarter chunk at a time: lane L holds the 8-point group 32m + ((L + m) & 31),
+//            m = 8s..8s+7, in registers (conflict-free scalar LDS, skewed ownership; 32 registers, so 32 warps fit an
+//            SM) and screens it against a block of queries with packed FP32x2 FMAs.  All that is kept per (query,
+//            group) is the group's MINIMUM (3-input FMNMX) as an order-preserving 16-bit key.  No compare, no
+//            branch, no shuffle.
+//   phase 2  a warp owns one query.  Its nchunks * 128 group keys are read as packed pairs: the packed minimum over
+//            a lane's words gives two minima of disjoint point sets per lane, 64 in all; their k-th smallest Tt
+//            proves that k points lie within Tt + |q|^2 + E, so only groups whose minimum is <= Tt + 2E can hold one
+//            of the k nearest -- about k groups.  They are compacted into a list and the warp evaluates FOUR listed
+//            groups per step with the reference expression (8 lanes each; the skewed ownership keeps the reads spread
+//            over the banks), appending `d <= Tt + |q|^2 + E` by ballot.  The <= 64 candidates are ordered exactly by
+//            order_candidates().  Anything unusual (more than 64 candidates or 128 groups: heavy ties, outliers that
+//            blow up E) takes the exact streaming selection instead.
 //
-// Work: a CTA of 16 warps = two groups of 8 warps, each with its own named barrier, query block and minima
-// buffer, so one group's phase 2 (shuffle-latency bound) overlaps the other's phase 1 (FP32 issue bound).  A
-// CTA is persistent over a contiguous range of query blocks and (re)loads the cloud only when it changes.
+// Error bound (u = 2^-24, all quantities non-negative reals unless marked _fp):
+//   |p|^2_fp = |p|^2 (1 + 3u); each of the three FMAs rounds a partial sum of magnitude <= |p|^2 + 2|p||q|, so
+//   |t_fp - t| <= 3u|p|^2 + 3u(|p|^2 + 2|p||q|) <= 6u(|p|+|q|)^2;  d_fp sums positive terms with five roundings on
+//   each path, |d_fp - d| <= 5.1u d <= 5.1u(|p|+|q|)^2;  |q|^2_fp is within 3u|q|^2.  Total 14.2u(|p|+|q|)^2 < E.
+//
+// Work: a CTA of 32 warps = two groups of 16 warps, each with its own named barrier, query block and key buffer; the
+// groups are started half a period apart so one group's phase 2 (shuffle-latency bound) overlaps the other's phase 1
+// (FP32-pipe bound).  Both phases are chains of dependent instructions: eight warps per scheduler hide them.  A CTA
+// is persistent over a contiguous range of query blocks and (re)loads the cloud only when it changes.
 //
 // Same distance expression, ordering and tie rule as knn_group_kernel (KNN_CUDA semantics).
 #pragma once
@@ -30,12 +41,13 @@
 
 namespace gm3d {
 
-constexpr int kKlChunk = 1024;          // points per chunk (32 per lane)
-constexpr int kKlChunkFloats = 3 * kKlChunk;
-constexpr int kKlGroupWarps = 8;        // warps per group
+constexpr int kKlChunk = 1024;              // points per chunk
+constexpr int kKlChunkFloats = 4 * kKlChunk;  // x | y | z | |p|^2
+constexpr int kKlGroupWarps = 16;           // warps per group
 constexpr int kKlThreads = 2 * kKlGroupWarps * 32;
-constexpr int kKlMaxN = 8 * kKlChunk;   // one warp of a group per chunk
-constexpr int kKlMaxList = 128;         // listed groups per query
+constexpr int kKlMaxN = 8 * kKlChunk;
+constexpr int kKlMaxList = 128;             // listed groups per query
+constexpr float kKlPad = 1e18f;             // padding coordinate: finite, its distances (~3e36) never pass anything
 
 struct KnnLargeParams {
     const float* ref;     // (B, N, 3)
@@ -59,83 +71,85 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
     asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
 }
-
-// Upper bound (as float bits) of the k-th smallest of the 64 truncated values packed in `both` (low and high
-// 16-bit halves) over the warp's lanes.
-__device__ __forceinline__ unsigned bound_from_minima16(unsigned both, int k, int lane) {
-    both = sort_u16x2(both, lane);
-    const unsigned rev = __shfl_sync(kFull, both, 31 - lane);
-    unsigned low = min(both & 0xffffu, rev >> 16);
-    unsigned tb;
-    if (k == 32) {
-        tb = __reduce_max_sync(kFull, low);
-    } else {
-        low = merge_u32(low, lane);
-        tb = __shfl_sync(kFull, low, k - 1);
-    }
-    return min((tb << 16) | 0xffffu, kFltMaxBits);
+// order-preserving unsigned key of a float (any sign) and its inverse
+__device__ __forceinline__ unsigned okey(float f) {
+    const unsigned b = __float_as_uint(f);
+    return b ^ (static_cast<unsigned>(static_cast<int>(b) >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float okey_inv(unsigned key) {
+    return __uint_as_float((key & 0x80000000u) ? (key ^ 0x80000000u) : ~key);
 }
 
-// phase 1 of one (chunk, query block): group minima of the lane's 32 points for queries q_first, q_first + q_step, ...
-// sc: the chunk in shared memory.  s_gm: minima of the block, [query][chunk][lane] 8-byte words.
-__device__ __forceinline__ void kl_chunk_minima(const float* __restrict__ sc, int chunk, int nchunks, int lane,
-                                                const float4* __restrict__ s_q, uint2* __restrict__ s_gm, int q_first,
-                                                int q_step, int nq) {
-    float2 X[16], Y[16], Z[16];
+// k-th smallest (as a 16-bit key) of the 64 keys packed in `both` (low and high halves) over the warp's lanes.
+__device__ __forceinline__ unsigned kth_of_64_keys(unsigned both, int k, int lane) {
+    both = sort_u16x2(both, lane);
+    const unsigned rev = __shfl_sync(kFull, both, 31 - lane);
+    unsigned low = min(both & 0xffffu, rev >> 16);  // the 32 smallest, as a bitonic sequence
+    if (k == 32) return __reduce_max_sync(kFull, low);
+    low = merge_u32(low, lane);
+    return __shfl_sync(kFull, low, k - 1);
+}
+
+// phase 1 of one (quarter chunk, query block): screen the lane's 8-point group against queries q_first, q_first +
+// q_step, ...  sc: the chunk in shared memory.  s_qa: (-2qx, -2qy, -2qz, E) per query.  s_gm: keys of the block,
+// [query][chunk][s][lane] 16-bit.
+__device__ __forceinline__ void kl_quarter_minima(const float* __restrict__ sc, int chunk, int s, int nchunks, int lane,
+                                                  const float4* __restrict__ s_qa, unsigned short* __restrict__ s_gm,
+                                                  int q_first, int q_step, int nq) {
+    float2 X[4], Y[4], Z[4], Wt[4];
 #pragma unroll
-    for (int h = 0; h < 16; ++h) {
-        const float* p0 = sc + 64 * h + ((lane + 2 * h) & 31);
-        const float* p1 = sc + 64 * h + 32 + ((lane + 2 * h + 1) & 31);
+    for (int h = 0; h < 4; ++h) {
+        const int m0 = 8 * s + 2 * h, m1 = m0 + 1;
+        const float* p0 = sc + 32 * m0 + ((lane + m0) & 31);
+        const float* p1 = sc + 32 * m1 + ((lane + m1) & 31);
         X[h] = make_float2(p0[0], p1[0]);
         Y[h] = make_float2(p0[kKlChunk], p1[kKlChunk]);
         Z[h] = make_float2(p0[2 * kKlChunk], p1[2 * kKlChunk]);
+        Wt[h] = make_float2(p0[3 * kKlChunk], p1[3 * kKlChunk]);
     }
+    unsigned short* out = s_gm + (chunk * 4 + s) * 32 + lane;
     for (int qi = q_first; qi < nq; qi += q_step) {
-        const float4 qv = s_q[qi];
-        const float2 q2x = make_float2(qv.x, qv.x), q2y = make_float2(qv.y, qv.y), q2z = make_float2(qv.z, qv.z);
-        unsigned mb[4];
+        const float4 qa = s_qa[qi];
+        const float2 ax = make_float2(qa.x, qa.x), ay = make_float2(qa.y, qa.y), az = make_float2(qa.z, qa.z);
+        float2 t[4];
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            float2 d[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                d[e] = sumsq_acc2(sub2(X[4 * s + e], q2x), sub2(Y[4 * s + e], q2y), sub2(Z[4 * s + e], q2z));
-            float m = fmin3(d[0].x, d[0].y, d[1].x);
-            m = fmin3(m, d[1].y, d[2].x);
-            m = fmin3(m, d[2].y, d[3].x);
-            mb[s] = __float_as_uint(fminf(m, d[3].y));
-        }
-        // upper halves (sign, exponent, 7 mantissa bits): still ordered, and `d <= T` for a bound T whose low half
-        // is all ones depends on the upper half alone
-        s_gm[(qi * nchunks + chunk) * 32 + lane] = make_uint2(__byte_perm(mb[0], mb[1], 0x7632), __byte_perm(mb[2], mb[3], 0x7632));
+        for (int e = 0; e < 4; ++e) t[e] = fma2(X[e], ax, fma2(Y[e], ay, fma2(Z[e], az, Wt[e])));
+        float m = fmin3(t[0].x, t[0].y, t[1].x);
+        m = fmin3(m, t[1].y, t[2].x);
+        m = fmin3(m, t[2].y, t[3].x);
+        out[qi * nchunks * 128] = static_cast<unsigned short>(okey(fminf(m, t[3].y)) >> 16);  // truncation rounds a key down
     }
 }
 
 __global__ void __launch_bounds__(kKlThreads, 1) knn_large_kernel(const KnnLargeParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = p.N, G = p.G, k = p.k, nchunks = p.nchunks, NQ = p.nq;
-    float* s_cloud = reinterpret_cast<float*>(smem_raw);                               // [nchunks][3][1024]
-    uint2* s_gm_all = reinterpret_cast<uint2*>(s_cloud + nchunks * kKlChunkFloats);    // [2][NQ][nchunks][32]
-    float4* s_q_all = reinterpret_cast<float4*>(s_gm_all + 2 * NQ * nchunks * 32);    // [2][NQ]
-    u64* s_cb_all = reinterpret_cast<u64*>(s_q_all + 2 * NQ);                          // [16 warps][64]
-    unsigned short* s_list_all = reinterpret_cast<unsigned short*>(s_cb_all + 2 * kKlGroupWarps * 64);  // [16][128]
+    float* s_cloud = reinterpret_cast<float*>(smem_raw);                                  // [nchunks][4][1024]
+    unsigned* s_gm_all = reinterpret_cast<unsigned*>(s_cloud + nchunks * kKlChunkFloats);  // [2][NQ][nchunks][4][32] 16-bit keys
+    float4* s_qa_all = reinterpret_cast<float4*>(s_gm_all + 2 * NQ * nchunks * 64);       // [2][NQ]
+    float4* s_qo_all = s_qa_all + 2 * NQ;                                                 // [2][NQ]
+    u64* s_cb_all = reinterpret_cast<u64*>(s_qo_all + 2 * NQ);                            // [32 warps][64]
+    unsigned short* s_list_all = reinterpret_cast<unsigned short*>(s_cb_all + 2 * kKlGroupWarps * 64);  // [32][128]
+    __shared__ float s_wmax[2 * kKlGroupWarps];  // per-warp max |p|^2 of the loaded cloud
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grp = warp / kKlGroupWarps, wg = warp % kKlGroupWarps, gtid = tid - grp * kKlGroupWarps * 32;
-    uint2* s_gm = s_gm_all + grp * NQ * nchunks * 32;
-    float4* s_q = s_q_all + grp * NQ;
+    unsigned* s_gm = s_gm_all + grp * NQ * nchunks * 64;
+    float4* s_qa = s_qa_all + grp * NQ;
+    float4* s_qo = s_qo_all + grp * NQ;
     u64* cb = s_cb_all + warp * 64;
     unsigned short* glist = s_list_all + warp * kKlMaxList;
-    const float inf = __uint_as_float(kInfBits);
 
     // contiguous range of query blocks of this CTA
     const long long tb = p.total_blocks;
     const int blk_begin = static_cast<int>(tb * blockIdx.x / gridDim.x);
     const int blk_end = static_cast<int>(tb * (blockIdx.x + 1) / gridDim.x);
 
-    // phase-1 roles inside a group: chunk = wg % nchunks, queries wg / nchunks + i * R
-    const int R = kKlGroupWarps / nchunks;
-    const int W = 2 * nchunks;  // 32-bit words of packed minima per lane in phase 2 (<= 16)
+    // phase-1 tasks of a block: (chunk, s) = (t >> 2, t & 3), t < 4 * nchunks.  Fewer tasks than warps: the
+    // warps of a task split the queries.
+    const int ntasks = 4 * nchunks;
+    const int R = ntasks < kKlGroupWarps ? kKlGroupWarps / ntasks : 1;
+    const int W = 2 * nchunks;  // 32-bit key words per lane in phase 2 (<= 16)
 
     bool staggered = false;
     int cur = blk_begin;
@@ -144,13 +158,19 @@ __global__ void __launch_bounds__(kKlThreads, 1) knn_large_kernel(const KnnLarge
         const int seg_end = min(blk_end, (b + 1) * p.nqb);
         const float* cloud = p.ref + static_cast<size_t>(b) * N * 3;
         __syncthreads();  // both groups are done with the previous cloud
+        float wmax = 0.f;
         for (int i = tid; i < nchunks * kKlChunk; i += kKlThreads) {
             const bool v = i < N;
             float* d = s_cloud + (i >> 10) * kKlChunkFloats + (i & (kKlChunk - 1));
-            d[0] = v ? __ldg(cloud + 3 * i + 0) : inf;
-            d[kKlChunk] = v ? __ldg(cloud + 3 * i + 1) : inf;
-            d[2 * kKlChunk] = v ? __ldg(cloud + 3 * i + 2) : inf;
+            const float x = v ? __ldg(cloud + 3 * i + 0) : kKlPad;
+            const float y = v ? __ldg(cloud + 3 * i + 1) : kKlPad;
+            const float z = v ? __ldg(cloud + 3 * i + 2) : kKlPad;
+            const float w = sumsq_acc(x, y, z);
+            d[0] = x, d[kKlChunk] = y, d[2 * kKlChunk] = z, d[3 * kKlChunk] = w;
+            if (v) wmax = fmaxf(wmax, w);
         }
+        wmax = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(wmax)));  // non-negative: bit order = value order
+        if (lane == 0) s_wmax[warp] = wmax;
         __syncthreads();
 
         for (int blk = cur + grp; blk < seg_end; blk += 2) {
@@ -165,26 +185,51 @@ __global__ void __launch_bounds__(kKlThreads, 1) knn_large_kernel(const KnnLarge
             const int nq = nparts == 1 ? nqb0 : (part == 0 ? nqb0 / 2 : nqb0 - nqb0 / 2);
             if (gtid < nq) {
                 const float* qp = p.query + (static_cast<size_t>(b) * G + q0 + gtid) * 3;
-                s_q[gtid] = make_float4(__ldg(qp), __ldg(qp + 1), __ldg(qp + 2), 0.f);
+                const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+                float S = s_wmax[0];
+#pragma unroll
+                for (int w = 1; w < 2 * kKlGroupWarps; ++w) S = fmaxf(S, s_wmax[w]);
+                const float cq = sumsq_acc(qx, qy, qz);
+                const float r = sqrtf(S) + sqrtf(cq);
+                const float E = fmaxf(24.f * 5.9604645e-8f * r * r, 1e-30f);
+                s_qa[gtid] = make_float4(-2.f * qx, -2.f * qy, -2.f * qz, E);
+                s_qo[gtid] = make_float4(qx, qy, qz, cq);
             }
             group_bar(grp);
-            if (wg < R * nchunks)
-                kl_chunk_minima(s_cloud + (wg % nchunks) * kKlChunkFloats, wg % nchunks, nchunks, lane, s_q, s_gm, wg / nchunks, R, nq);
+            if (ntasks < kKlGroupWarps) {
+                if (wg < R * ntasks) {
+                    const int t = wg % ntasks;
+                    kl_quarter_minima(s_cloud + (t >> 2) * kKlChunkFloats, t >> 2, t & 3, nchunks, lane, s_qa,
+                                      reinterpret_cast<unsigned short*>(s_gm), wg / ntasks, R, nq);
+                }
+            } else {
+                for (int t = wg; t < ntasks; t += kKlGroupWarps)
+                    kl_quarter_minima(s_cloud + (t >> 2) * kKlChunkFloats, t >> 2, t & 3, nchunks, lane, s_qa,
+                                      reinterpret_cast<unsigned short*>(s_gm), 0, 1, nq);
+            }
             group_bar(grp);
 
             for (int qi = wg; qi < nq; qi += kKlGroupWarps) {
-                const float4 qv = s_q[qi];
-                // this lane's share of the query's packed minima: words lane + 32 i, i < W (group id = 2 * word + half)
-                const unsigned* gw = reinterpret_cast<const unsigned*>(s_gm + qi * nchunks * 32) + lane;
+                const float4 qv = s_qo[qi];
+                const float E = s_qa[qi].w;
+                // this lane's share of the query's keys: 32-bit words lane + 32 i, i < W, two keys each.  Key g of a
+                // query belongs to the group (chunk, s, owner lane) = (g >> 7, (g >> 5) & 3, g & 31).
+                const unsigned* gw = s_gm + qi * nchunks * 64 + lane;
                 unsigned both = 0xffffffffu;
                 for (int i = 0; i < W; ++i) both = __vminu2(both, gw[32 * i]);
-                const unsigned tbits = bound_from_minima16(both, k, lane);
-                // groups that can hold a candidate -> compact list (flat group id = chunk * 128 + owner lane * 4 + s)
-                unsigned gm = 0;
+                const unsigned kk = kth_of_64_keys(both, k, lane);
+                // k points have t <= Tt, hence reference distance <= Tt + |q|^2 + E =: Tup; any point that close has
+                // t <= Tt + 2E =: theta.  (The extra E / 2 in Tup covers the roundings of the two additions.)
+                const float Tt = okey_inv((kk << 16) | 0xffffu);
+                const float theta = Tt + 2.f * E;
+                const float Tup = (Tt + qv.w) + 1.5f * E;
+                const unsigned thb = okey(theta) | 0xffffu;  // word-level compare: low half all ones
+                const bool sane = theta < __uint_as_float(kInfBits) && Tup < __uint_as_float(kInfBits);
+                unsigned gm = 0;  // bit 2i: low-half group of word i, bit 2i + 1: high-half group
                 for (int i = 0; i < W; ++i) {
                     const unsigned w = gw[32 * i];
-                    if ((w << 16) <= tbits) gm |= 1u << (2 * i);
-                    if (w <= tbits) gm |= 2u << (2 * i);
+                    if ((w << 16) <= thb) gm |= 1u << (2 * i);
+                    if (w <= thb) gm |= 2u << (2 * i);
                 }
                 const int mine = __popc(gm);
                 int incl = mine;
@@ -195,8 +240,10 @@ __global__ void __launch_bounds__(kKlThreads, 1) knn_large_kernel(const KnnLarge
                 }
                 const int ng = __shfl_sync(kFull, incl, 31);
                 int total = 0;
-                if (ng <= kKlMaxList) {
+                const bool fast = sane && ng <= kKlMaxList;
+                if (fast) {
                     int off = incl - mine;
+                    // list entry: key index g = (word index within the query) * 2 + {0: low, 1: high}
                     while (gm) {
                         const int bit = __ffs(gm) - 1;
                         gm &= gm - 1;
@@ -208,26 +255,26 @@ __global__ void __launch_bounds__(kKlThreads, 1) knn_large_kernel(const KnnLarge
                     for (int e0 = 0; e0 < ng && total <= 64; e0 += 4) {
                         const bool valid = e0 + sub < ng;
                         const int g = valid ? glist[e0 + sub] : 0;
-                        const int m = 8 * (g & 3) + r;
-                        // mapped index: chunk * 3072 + position in the chunk
-                        const int o = (g >> 7) * kKlChunkFloats + 32 * m + ((((g >> 2) & 31) + m) & 31);
+                        const int m = ((g >> 2) & 24) + r;  // 8 s + r
+                        // mapped index: chunk * 4096 + position in the chunk
+                        const int o = (g >> 7) * kKlChunkFloats + 32 * m + (((g & 31) + m) & 31);
                         const float* pp = s_cloud + o;
                         const float d = sumsq_acc(__fsub_rn(pp[0], qv.x), __fsub_rn(pp[kKlChunk], qv.y), __fsub_rn(pp[2 * kKlChunk], qv.z));
-                        const bool pass = valid && __float_as_uint(d) <= tbits;
+                        const bool pass = valid && d <= Tup;
                         const unsigned pb = __ballot_sync(kFull, pass);
                         if (pass) cl[total + __popc(pb & ((1u << lane) - 1u))] = static_cast<unsigned short>(o);  // < 64 + 32 slots
                         total += __popc(pb);
                     }
                 }
                 u64 top;
-                if (ng <= kKlMaxList && total <= 64) {
+                if (fast && total <= 64) {
                     float thr;
                     order_candidates(s_cloud, s_cloud + kKlChunk, s_cloud + 2 * kKlChunk, 0, total, make_float2(qv.x, qv.x),
                                      make_float2(qv.y, qv.y), make_float2(qv.z, qv.z), k, lane, cb, top, thr);
                     // mapped -> point index (same order, so ties were broken by the lower point index)
                     const unsigned o = static_cast<unsigned>(top & 0xffffffffu);
-                    top = (top & 0xffffffff00000000ull) | (o - (o / kKlChunkFloats) * (2 * kKlChunk));
-                } else {  // heavy ties: exact streaming selection over the whole cloud
+                    top = (top & 0xffffffff00000000ull) | ((o >> 12) << 10) | (o & (kKlChunk - 1));
+                } else {  // heavy ties / outliers: exact streaming selection over the whole cloud
                     __syncwarp();
                     top = kKeyInf;
                     float thr = __uint_as_float(kFltMaxBits);
@@ -258,7 +305,7 @@ __global__ void __launch_bounds__(kKlThreads, 1) knn_large_kernel(const KnnLarge
                     }
                 }
             }
-            group_bar(grp);  // minima and queries of this block are dead
+            group_bar(grp);  // keys and queries of this block are dead
           }
         }
         cur = seg_end;
@@ -266,8 +313,8 @@ __global__ void __launch_bounds__(kKlThreads, 1) knn_large_kernel(const KnnLarge
 }
 
 inline size_t knn_large_smem_bytes(int nchunks, int nq) {
-    return static_cast<size_t>(nchunks) * kKlChunk * 12 + static_cast<size_t>(2) * nq * nchunks * 32 * 8 +
-           static_cast<size_t>(2) * nq * 16 + static_cast<size_t>(2 * kKlGroupWarps) * (64 * 8 + kKlMaxList * 2);
+    return static_cast<size_t>(nchunks) * kKlChunk * 16 + static_cast<size_t>(2) * nq * nchunks * 64 * 4 +
+           static_cast<size_t>(4) * nq * 16 + static_cast<size_t>(2 * kKlGroupWarps) * (64 * 8 + kKlMaxList * 2);
 }
 
 // Returns GM3D_ENOSUP when the shape is outside this kernel's range (the caller falls back to the streaming kernel).
@@ -278,9 +325,9 @@ static int launch_knn_large(const float* ref, const float* query, int B, int N, 
     p.ref = ref, p.query = query, p.dist_out = dist, p.idx_out = idx, p.nbhd = nbhd, p.nbhd_org = nbhd_org;
     p.N = N, p.G = G, p.k = k;
     p.nchunks = (N + kKlChunk - 1) / kKlChunk;
-    const size_t budget = 227 * 1024 - 1024;
+    const size_t budget = 227 * 1024 - 1024 - 256;
     int nq = 32;
-    // smaller query blocks when the problem would leave SMs without a block, or when the minima do not fit
+    // smaller query blocks when the problem would leave SMs without a block, or when the keys do not fit
     while (nq > 8 && static_cast<long long>(B) * ((G + nq - 1) / nq) < 2 * 148) nq >>= 1;
     while (nq > 8 && knn_large_smem_bytes(p.nchunks, nq) > budget) nq >>= 1;
     if (knn_large_smem_bytes(p.nchunks, nq) > budget) return GM3D_ENOSUP;

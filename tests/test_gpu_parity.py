@@ -155,6 +155,23 @@ def test_knn_large_two_phase_edges(cuda, B, N, G, k):
     assert np.array_equal(host(D).view(np.uint32), Dw.view(np.uint32))
 
 
+@pytest.mark.parametrize("shift,scale", [(0.0, 1.0), (3.0, 1.0), (30.0, 1.0), (1000.0, 1.0), (0.0, 1e-12), (0.0, 1e9), (5e4, 50.0)])
+def test_knn_large_screen_margin(cuda, shift, scale):
+    """The two-phase kernel screens points with |p|^2 - 2 p.q (three FMAs) and keeps an error margin E ~ (|p|+|q|)^2:
+    clouds far from the origin (cancellation: E comparable to or larger than the neighbour distances), tiny and huge
+    scales must still give the oracle's indices bit for bit (through the margin or the exact fallback)."""
+    from gm3d_b200.knn import KNN
+    B, N, G, k = 2, 4096, 96, 32
+    xyz = (synthetic_clouds(B, N, 77, "sphere") * np.float32(scale) + np.float32(shift)).astype(np.float32)
+    rng = np.random.default_rng(11)
+    q = np.stack([xyz[b, rng.choice(N, G, replace=False)] for b in range(B)])
+    q[:, ::2] += (rng.standard_normal((B, q[:, ::2].shape[1], 3)) * 0.03 * scale).astype(np.float32)
+    D, I = KNN(k, transpose_mode=True)(dev(xyz, cuda), dev(q, cuda))
+    Dw, Iw = co.knn(xyz, q, k)
+    assert np.array_equal(host(I), Iw)
+    assert np.array_equal(host(D).view(np.uint32), Dw.view(np.uint32))
+
+
 def test_knn_large_heavy_ties(cuda):
     """More than 64 points within the bound (duplicates, lattice distances): the exact streaming fallback inside the
     two-phase kernel, and bit-equal distances among the best k+1 (64-bit key ordering)."""
