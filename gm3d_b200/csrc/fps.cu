@@ -17,7 +17,17 @@ namespace gm3d {
 
 constexpr int kFpsMaxRegN = 8192;  // largest N served by the register-resident kernel
 
-template <int THREADS, int PPT>
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+// TWO_STAGE (many points per thread): the round's maximum VALUE is reduced first (3-input FMNMX per thread, one
+// REDUX per warp, one barrier), and only the warp(s) holding that value look for its lowest point index -- the
+// per-thread arg-max tournament (3 ALU-pipe instructions per point in every warp) is gone, at the price of a
+// second barrier per round.
+template <int THREADS, int PPT, bool TWO_STAGE = false>
 __global__ void __launch_bounds__(THREADS, 1)
     fps_reg_kernel(const float* __restrict__ xyz, int N, int G, int32_t* __restrict__ idx,
                    float* __restrict__ centers, int use_bulk) {
@@ -27,10 +37,12 @@ __global__ void __launch_bounds__(THREADS, 1)
     const int n4 = (N + 3) & ~3;
     int* s_sel = reinterpret_cast<int*>(s_xyz + 3 * n4);
     __shared__ int2 s_red[2][32];
+    __shared__ int s_best[2];
     __shared__ __align__(8) uint64_t s_bar;
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* cloud = xyz + static_cast<size_t>(b) * N * 3;
+    if (tid == 0) s_best[0] = s_best[1] = INT_MAX;
 
     if (use_bulk) {
         if (tid == 0) {
@@ -78,6 +90,27 @@ __global__ void __launch_bounds__(THREADS, 1)
             T[h].x = fminf(d.x, T[h].x);
             T[h].y = fminf(d.y, T[h].y);
             m[2 * h] = T[h].x, m[2 * h + 1] = T[h].y;
+        }
+        if (TWO_STAGE) {
+            float mx = fmaxf(m[0], m[1]);
+#pragma unroll
+            for (int s2 = 2; s2 < PPT; s2 += 2) mx = fmax3(mx, m[s2], m[s2 + 1]);
+            const int vmax = __reduce_max_sync(kFull, f2ord(mx));
+            if (lane == 0) s_red[j & 1][warp].x = vmax;
+            __syncthreads();
+            if (tid == 0) s_best[(j + 1) & 1] = INT_MAX;  // next round's slot; its last readers are past this barrier
+            const int gmax = __reduce_max_sync(kFull, red_rd[(j & 1) * 32].x);
+            if (vmax == gmax) {  // warp-uniform: this warp holds a maximum; lowest point index among its holders
+                int besti = INT_MAX;
+#pragma unroll
+                for (int s2 = PPT - 1; s2 >= 0; --s2) besti = f2ord(m[s2]) == gmax ? s2 * THREADS + tid : besti;
+                const int kmin = __reduce_min_sync(kFull, besti);
+                if (lane == 0) atomicMin(&s_best[j & 1], kmin);
+            }
+            __syncthreads();
+            old = s_best[j & 1];
+            if (tid == 0) s_sel[j] = old;
+            continue;
         }
         // thread arg-max, lowest slot (= lowest point index of the thread) on ties: pairwise tournament
         int mi[PPT];
@@ -172,11 +205,11 @@ __global__ void __launch_bounds__(1024, 1)
     }
 }
 
-template <int THREADS, int PPT>
+template <int THREADS, int PPT, bool TWO_STAGE = false>
 static int launch_fps_reg(const float* xyz, int B, int N, int G, int32_t* idx, float* centers, cudaStream_t st) {
     const int n4 = (N + 3) & ~3;
     const size_t smem = static_cast<size_t>(n4) * 12 + static_cast<size_t>(G) * 4;
-    auto kern = fps_reg_kernel<THREADS, PPT>;
+    auto kern = fps_reg_kernel<THREADS, PPT, TWO_STAGE>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return static_cast<int>(e);
@@ -210,7 +243,13 @@ GM3D_API int gm3d_fps_f32(const float* xyz, int B, int N, int G, int32_t* idx, f
     if (N <= 256) return launch_fps_reg<64, 4>(xyz, B, N, G, idx, centers, st);
     if (N <= 512) return launch_fps_reg<128, 4>(xyz, B, N, G, idx, centers, st);
     if (N <= 1024) return variant == 1 ? launch_fps_reg<256, 4>(xyz, B, N, G, idx, centers, st) : launch_fps_reg<128, 8>(xyz, B, N, G, idx, centers, st);
-    if (N <= 2048) return variant == 1 ? launch_fps_reg<512, 4>(xyz, B, N, G, idx, centers, st) : launch_fps_reg<256, 8>(xyz, B, N, G, idx, centers, st);
-    if (N <= 4096) return launch_fps_reg<512, 8>(xyz, B, N, G, idx, centers, st);
-    return variant == 1 ? launch_fps_reg<1024, 8>(xyz, B, N, G, idx, centers, st) : launch_fps_reg<512, 16>(xyz, B, N, G, idx, centers, st);
+    if (N <= 2048) {
+        if (variant == 4) return launch_fps_reg<256, 8, true>(xyz, B, N, G, idx, centers, st);
+        return variant == 1 ? launch_fps_reg<512, 4>(xyz, B, N, G, idx, centers, st) : launch_fps_reg<256, 8>(xyz, B, N, G, idx, centers, st);
+    }
+    if (N <= 4096) return variant == 4 ? launch_fps_reg<512, 8, true>(xyz, B, N, G, idx, centers, st) : launch_fps_reg<512, 8>(xyz, B, N, G, idx, centers, st);
+    if (variant == 1) return launch_fps_reg<1024, 8>(xyz, B, N, G, idx, centers, st);
+    if (variant == 2) return launch_fps_reg<512, 16>(xyz, B, N, G, idx, centers, st);
+    if (variant == 3) return launch_fps_reg<1024, 8, true>(xyz, B, N, G, idx, centers, st);
+    return launch_fps_reg<512, 16, true>(xyz, B, N, G, idx, centers, st);
 }
