@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(kKlThreads, 1) knn_large_kernel(const KnnLarge
                 // query belongs to the group (chunk, s, owner lane) = (g >> 7, (g >> 5) & 3, g & 31).
                 const unsigned* gw = s_gm + qi * nchunks * 64 + lane;
                 unsigned both = 0xffffffffu;
+#pragma unroll 4
                 for (int i = 0; i < W; ++i) both = __vminu2(both, gw[32 * i]);
                 const unsigned kk = kth_of_64_keys(both, k, lane);
                 // k points have t <= Tt, hence reference distance <= Tt + |q|^2 + E =: Tup; any point that close has
@@ -226,6 +227,7 @@ __global__ void __launch_bounds__(kKlThreads, 1) knn_large_kernel(const KnnLarge
                 const unsigned thb = okey(theta) | 0xffffu;  // word-level compare: low half all ones
                 const bool sane = theta < __uint_as_float(kInfBits) && Tup < __uint_as_float(kInfBits);
                 unsigned gm = 0;  // bit 2i: low-half group of word i, bit 2i + 1: high-half group
+#pragma unroll 4
                 for (int i = 0; i < W; ++i) {
                     const unsigned w = gw[32 * i];
                     if ((w << 16) <= thb) gm |= 1u << (2 * i);
@@ -252,18 +254,25 @@ __global__ void __launch_bounds__(kKlThreads, 1) knn_large_kernel(const KnnLarge
                     __syncwarp();
                     unsigned short* cl = reinterpret_cast<unsigned short*>(cb);
                     const int sub = lane >> 3, r = lane & 7;
-                    for (int e0 = 0; e0 < ng && total <= 64; e0 += 4) {
-                        const bool valid = e0 + sub < ng;
-                        const int g = valid ? glist[e0 + sub] : 0;
-                        const int m = ((g >> 2) & 24) + r;  // 8 s + r
+                    // eight listed groups per step (two per quarter warp): two independent chains per lane
+                    for (int e0 = 0; e0 < ng && total <= 64; e0 += 8) {
+                        const bool valid0 = e0 + sub < ng, valid1 = e0 + 4 + sub < ng;
+                        const int g0 = valid0 ? glist[e0 + sub] : 0, g1 = valid1 ? glist[e0 + 4 + sub] : 0;
+                        const int m0 = ((g0 >> 2) & 24) + r, m1 = ((g1 >> 2) & 24) + r;  // 8 s + r
                         // mapped index: chunk * 4096 + position in the chunk
-                        const int o = (g >> 7) * kKlChunkFloats + 32 * m + (((g & 31) + m) & 31);
-                        const float* pp = s_cloud + o;
-                        const float d = sumsq_acc(__fsub_rn(pp[0], qv.x), __fsub_rn(pp[kKlChunk], qv.y), __fsub_rn(pp[2 * kKlChunk], qv.z));
-                        const bool pass = valid && d <= Tup;
-                        const unsigned pb = __ballot_sync(kFull, pass);
-                        if (pass) cl[total + __popc(pb & ((1u << lane) - 1u))] = static_cast<unsigned short>(o);  // < 64 + 32 slots
-                        total += __popc(pb);
+                        const int o0 = (g0 >> 7) * kKlChunkFloats + 32 * m0 + (((g0 & 31) + m0) & 31);
+                        const int o1 = (g1 >> 7) * kKlChunkFloats + 32 * m1 + (((g1 & 31) + m1) & 31);
+                        const float* pp0 = s_cloud + o0;
+                        const float* pp1 = s_cloud + o1;
+                        const float d0 = sumsq_acc(__fsub_rn(pp0[0], qv.x), __fsub_rn(pp0[kKlChunk], qv.y), __fsub_rn(pp0[2 * kKlChunk], qv.z));
+                        const float d1 = sumsq_acc(__fsub_rn(pp1[0], qv.x), __fsub_rn(pp1[kKlChunk], qv.y), __fsub_rn(pp1[2 * kKlChunk], qv.z));
+                        const bool pass0 = valid0 && d0 <= Tup, pass1 = valid1 && d1 <= Tup;
+                        const unsigned pb0 = __ballot_sync(kFull, pass0), pb1 = __ballot_sync(kFull, pass1);
+                        const unsigned lt = (1u << lane) - 1u;
+                        const int n0 = __popc(pb0);
+                        if (pass0) cl[total + __popc(pb0 & lt)] = static_cast<unsigned short>(o0);  // < 64 + 64 slots
+                        if (pass1) cl[total + n0 + __popc(pb1 & lt)] = static_cast<unsigned short>(o1);
+                        total += n0 + __popc(pb1);
                     }
                 }
                 u64 top;

@@ -13,6 +13,8 @@ adds the host<->device copies from/to pinned memory (the end-to-end arm of bench
 """
 from __future__ import annotations
 
+import os
+
 from typing import Optional
 
 import torch
@@ -36,6 +38,8 @@ class GroupLossStep:
         # B200: C1, C2, C4, M2AE levels 1-2 yes -- small batches included, because overlapped steps share the
         # GPU; M2AE level 0 with G=512 x 2 tiles no)
         worth = G * ((N + 1023) // 1024) <= 256
+        if fused is None and os.environ.get("GM3D_STEP_FUSED") in ("0", "1"):  # tuning aid (A/B runs of the two paths)
+            fused = os.environ["GM3D_STEP_FUSED"] == "1" and can_fuse
         self.fused = (can_fuse and worth) if fused is None else fused
         self.kernels_per_step = 1 if self.fused else KERNELS_PER_STEP
         self.dev = torch.device(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
