@@ -439,8 +439,10 @@ def run_native(args, cfg):
                 "config": {"workload": desc, "B_per_gpu": B, "N": N, "G": G, "k": k, "M": M,
                            "l2_policy": f"inputs larger than L2: ring of {ring} buffer sets x {per_set / 1e6:.1f} MB",
                            "cuda_graph": True,
-                           "step_overlap": (f"programmatic dependent launch inside graphs of up to {ring} steps"
-                                            if overlap and steps[0].fused else "none"),
+                           "step_overlap": ((f"programmatic dependent launch inside graphs of up to {ring} steps"
+                                             if steps[0].fused else
+                                             f"independent steps round-robin on {os.environ.get('GM3D_RING_LANES', '4')} forked streams "
+                                             f"inside graphs of up to {ring} steps") if overlap else "none"),
                            "kernels_per_step": steps[0].kernels_per_step, "collective": collective},
                 "clocks": clk, "e2e": e2e, "gpu_launches": steps[0].kernels_per_step * K,
                 "roofline": roofline, "roofline_detail": detail,

@@ -37,14 +37,16 @@
 // Same distance expression, ordering and tie rule as knn_group_kernel (KNN_CUDA semantics).
 #pragma once
 
+#include <stdlib.h>
+
 #include "knn_select.cuh"
 
 namespace gm3d {
 
 constexpr int kKlChunk = 1024;              // points per chunk
 constexpr int kKlChunkFloats = 4 * kKlChunk;  // x | y | z | |p|^2
-constexpr int kKlGroupWarps = 16;           // warps per group
-constexpr int kKlThreads = 2 * kKlGroupWarps * 32;
+constexpr int kKlMaxGroupWarps = 16;        // warps per group (GM3D_KL_GW: fewer, for co-residency experiments)
+constexpr int kKlMaxThreads = 2 * kKlMaxGroupWarps * 32;
 constexpr int kKlMaxN = 8 * kKlChunk;
 constexpr int kKlMaxList = 128;             // listed groups per query
 constexpr float kKlPad = 1e18f;             // padding coordinate: finite, its distances (~3e36) never pass anything
@@ -63,8 +65,8 @@ struct KnnLargeParams {
     int total_blocks;     // B * nqb
 };
 
-__device__ __forceinline__ void group_bar(int grp) {
-    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(kKlGroupWarps * 32) : "memory");
+__device__ __forceinline__ void group_bar(int grp, int group_threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(group_threads) : "memory");
 }
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
     float r;
@@ -121,19 +123,20 @@ __device__ __forceinline__ void kl_quarter_minima(const float* __restrict__ sc, 
     }
 }
 
-__global__ void __launch_bounds__(kKlThreads, 1) knn_large_kernel(const KnnLargeParams p) {
+__global__ void __launch_bounds__(kKlMaxThreads, 1) knn_large_kernel(const KnnLargeParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = p.N, G = p.G, k = p.k, nchunks = p.nchunks, NQ = p.nq;
+    const int nthreads = blockDim.x, GW = nthreads >> 6;  // two groups of GW warps
     float* s_cloud = reinterpret_cast<float*>(smem_raw);                                  // [nchunks][4][1024]
     unsigned* s_gm_all = reinterpret_cast<unsigned*>(s_cloud + nchunks * kKlChunkFloats);  // [2][NQ][nchunks][4][32] 16-bit keys
     float4* s_qa_all = reinterpret_cast<float4*>(s_gm_all + 2 * NQ * nchunks * 64);       // [2][NQ]
     float4* s_qo_all = s_qa_all + 2 * NQ;                                                 // [2][NQ]
     u64* s_cb_all = reinterpret_cast<u64*>(s_qo_all + 2 * NQ);                            // [32 warps][64]
-    unsigned short* s_list_all = reinterpret_cast<unsigned short*>(s_cb_all + 2 * kKlGroupWarps * 64);  // [32][128]
-    __shared__ float s_wmax[2 * kKlGroupWarps];  // per-warp max |p|^2 of the loaded cloud
+    unsigned short* s_list_all = reinterpret_cast<unsigned short*>(s_cb_all + 2 * GW * 64);  // [warps][128]
+    __shared__ float s_wmax[2 * kKlMaxGroupWarps];  // per-warp max |p|^2 of the loaded cloud
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int grp = warp / kKlGroupWarps, wg = warp % kKlGroupWarps, gtid = tid - grp * kKlGroupWarps * 32;
+    const int grp = warp / GW, wg = warp % GW, gtid = tid - grp * GW * 32;
     unsigned* s_gm = s_gm_all + grp * NQ * nchunks * 64;
     float4* s_qa = s_qa_all + grp * NQ;
     float4* s_qo = s_qo_all + grp * NQ;
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(kKlThreads, 1) knn_large_kernel(const KnnLarge
     // phase-1 tasks of a block: (chunk, s) = (t >> 2, t & 3), t < 4 * nchunks.  Fewer tasks than warps: the
     // warps of a task split the queries.
     const int ntasks = 4 * nchunks;
-    const int R = ntasks < kKlGroupWarps ? kKlGroupWarps / ntasks : 1;
+    const int R = ntasks < GW ? GW / ntasks : 1;
     const int W = 2 * nchunks;  // 32-bit key words per lane in phase 2 (<= 16)
 
     bool staggered = false;
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(kKlThreads, 1) knn_large_kernel(const KnnLarge
         const float* cloud = p.ref + static_cast<size_t>(b) * N * 3;
         __syncthreads();  // both groups are done with the previous cloud
         float wmax = 0.f;
-        for (int i = tid; i < nchunks * kKlChunk; i += kKlThreads) {
+        for (int i = tid; i < nchunks * kKlChunk; i += nthreads) {
             const bool v = i < N;
             float* d = s_cloud + (i >> 10) * kKlChunkFloats + (i & (kKlChunk - 1));
             const float x = v ? __ldg(cloud + 3 * i + 0) : kKlPad;
@@ -188,28 +191,28 @@ __global__ void __launch_bounds__(kKlThreads, 1) knn_large_kernel(const KnnLarge
                 const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
                 float S = s_wmax[0];
 #pragma unroll
-                for (int w = 1; w < 2 * kKlGroupWarps; ++w) S = fmaxf(S, s_wmax[w]);
+                for (int w = 1; w < 2 * kKlMaxGroupWarps; ++w) S = fmaxf(S, w < 2 * GW ? s_wmax[w] : 0.f);
                 const float cq = sumsq_acc(qx, qy, qz);
                 const float r = sqrtf(S) + sqrtf(cq);
                 const float E = fmaxf(24.f * 5.9604645e-8f * r * r, 1e-30f);
                 s_qa[gtid] = make_float4(-2.f * qx, -2.f * qy, -2.f * qz, E);
                 s_qo[gtid] = make_float4(qx, qy, qz, cq);
             }
-            group_bar(grp);
-            if (ntasks < kKlGroupWarps) {
+            group_bar(grp, GW * 32);
+            if (ntasks < GW) {
                 if (wg < R * ntasks) {
                     const int t = wg % ntasks;
                     kl_quarter_minima(s_cloud + (t >> 2) * kKlChunkFloats, t >> 2, t & 3, nchunks, lane, s_qa,
                                       reinterpret_cast<unsigned short*>(s_gm), wg / ntasks, R, nq);
                 }
             } else {
-                for (int t = wg; t < ntasks; t += kKlGroupWarps)
+                for (int t = wg; t < ntasks; t += GW)
                     kl_quarter_minima(s_cloud + (t >> 2) * kKlChunkFloats, t >> 2, t & 3, nchunks, lane, s_qa,
                                       reinterpret_cast<unsigned short*>(s_gm), 0, 1, nq);
             }
-            group_bar(grp);
+            group_bar(grp, GW * 32);
 
-            for (int qi = wg; qi < nq; qi += kKlGroupWarps) {
+            for (int qi = wg; qi < nq; qi += GW) {
                 const float4 qv = s_qo[qi];
                 const float E = s_qa[qi].w;
                 // this lane's share of the query's keys: 32-bit words lane + 32 i, i < W, two keys each.  Key g of a
@@ -314,16 +317,16 @@ __global__ void __launch_bounds__(kKlThreads, 1) knn_large_kernel(const KnnLarge
                     }
                 }
             }
-            group_bar(grp);  // keys and queries of this block are dead
+            group_bar(grp, GW * 32);  // keys and queries of this block are dead
           }
         }
         cur = seg_end;
     }
 }
 
-inline size_t knn_large_smem_bytes(int nchunks, int nq) {
+inline size_t knn_large_smem_bytes(int nchunks, int nq, int gw) {
     return static_cast<size_t>(nchunks) * kKlChunk * 16 + static_cast<size_t>(2) * nq * nchunks * 64 * 4 +
-           static_cast<size_t>(4) * nq * 16 + static_cast<size_t>(2 * kKlGroupWarps) * (64 * 8 + kKlMaxList * 2);
+           static_cast<size_t>(4) * nq * 16 + static_cast<size_t>(2 * gw) * (64 * 8 + kKlMaxList * 2);
 }
 
 // Returns GM3D_ENOSUP when the shape is outside this kernel's range (the caller falls back to the streaming kernel).
@@ -335,21 +338,23 @@ static int launch_knn_large(const float* ref, const float* query, int B, int N, 
     p.N = N, p.G = G, p.k = k;
     p.nchunks = (N + kKlChunk - 1) / kKlChunk;
     const size_t budget = 227 * 1024 - 1024 - 256;
+    static const int env_gw = getenv("GM3D_KL_GW") ? atoi(getenv("GM3D_KL_GW")) : 0;  // tuning aid: 4..16, even
+    const int gw = env_gw >= 4 && env_gw <= 16 && env_gw % 2 == 0 ? env_gw : 16;
     int nq = 32;
     // smaller query blocks when the problem would leave SMs without a block, or when the keys do not fit
     while (nq > 8 && static_cast<long long>(B) * ((G + nq - 1) / nq) < 2 * 148) nq >>= 1;
-    while (nq > 8 && knn_large_smem_bytes(p.nchunks, nq) > budget) nq >>= 1;
-    if (knn_large_smem_bytes(p.nchunks, nq) > budget) return GM3D_ENOSUP;
+    while (nq > 8 && knn_large_smem_bytes(p.nchunks, nq, gw) > budget) nq >>= 1;
+    if (knn_large_smem_bytes(p.nchunks, nq, gw) > budget) return GM3D_ENOSUP;
     p.nq = nq;
     p.nqb = (G + nq - 1) / nq;
     const long long total = static_cast<long long>(B) * p.nqb;
     if (total > 0x7fffffffLL) return GM3D_ENOSUP;
     p.total_blocks = static_cast<int>(total);
     const int grid = static_cast<int>(total < 2 * 148 ? (total + 1) / 2 : 148);
-    const size_t smem = knn_large_smem_bytes(p.nchunks, nq);
+    const size_t smem = knn_large_smem_bytes(p.nchunks, nq, gw);
     cudaError_t e = cudaFuncSetAttribute(knn_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
-    knn_large_kernel<<<grid, kKlThreads, smem, st>>>(p);
+    knn_large_kernel<<<grid, 2 * gw * 32, smem, st>>>(p);
     return launch_status();
 }
 

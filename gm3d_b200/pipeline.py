@@ -180,14 +180,36 @@ class StepRing:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.reduce_stats = reduce_stats
         self.head = torch.zeros((len(self.steps), 3), dtype=torch.float32, device=self.steps[0].dev) if reduce_stats else None
+        self._lanes = None
 
     def enqueue(self) -> None:
         n = len(self.steps)
-        for i, s in enumerate(self.steps):
-            f = 0
-            if s.fused and n > 1:
-                f = (_lib.STEP_OVERLAP_NEXT if i + 1 < n else 0) | (_lib.STEP_OVERLAP_PREV if i > 0 else 0)
-            s.enqueue(f)
+        s0 = self.steps[0]
+        nl = max(1, min(n, int(os.environ.get("GM3D_RING_LANES", "4"))))  # tuning aid; 1 = one stream
+        if not s0.fused and nl > 1:
+            # Kernel-sequence steps: the steps go round-robin to forked streams, so the FPS chain of one step -- G
+            # dependent rounds, one CTA per cloud, issue slots half empty -- runs beside the kNN / Chamfer kernels of
+            # another wherever SM resources allow (FPS CTAs of different steps pair up at N <= 2048; at N = 8192 the
+            # 20 SMs a 128-cloud FPS leaves free, and the tails of every kernel, get used).  The steps share no buffer.
+            main = torch.cuda.current_stream(s0.dev)
+            if self._lanes is None or len(self._lanes) != nl:
+                self._lanes = [torch.cuda.Stream(s0.dev) for _ in range(nl)]
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for li, lane in enumerate(self._lanes):
+                lane.wait_event(fork)
+                with torch.cuda.stream(lane):
+                    for s in self.steps[li::nl]:
+                        s.enqueue(0)
+                join = torch.cuda.Event()
+                join.record(lane)
+                main.wait_event(join)
+        else:
+            for i, s in enumerate(self.steps):
+                f = 0
+                if s.fused and n > 1:
+                    f = (_lib.STEP_OVERLAP_NEXT if i + 1 < n else 0) | (_lib.STEP_OVERLAP_PREV if i > 0 else 0)
+                s.enqueue(f)
         if self.reduce_stats:
             import torch.distributed as dist
             torch.stack([s.stats[:3] for s in self.steps], out=self.head)

@@ -629,6 +629,37 @@ def test_step_ring_overlapped_steps_equal_serial_steps(cuda):
             assert np.array_equal(host(getattr(s, n)), v), n
 
 
+def test_step_ring_kernel_sequence_lanes_equal_serial_steps(cuda):
+    """Kernel-sequence steps (N > 2048 or many groups) replayed as one graph with the steps spread round-robin over
+    forked streams: every step still gives the bits of the same step run alone, and the oracle's grouping."""
+    from gm3d_b200.pipeline import GroupLossStep, StepRing
+    B, N, G, k = 6, 4096, 96, 32
+    rng = np.random.default_rng(19)
+    steps, want, clouds = [], [], []
+    for r in range(7):
+        s = GroupLossStep(B, N, G, k, 0.6, device=cuda, seed=4, rand_offset=r * B * G)
+        assert not s.fused
+        clouds.append(synthetic_clouds(B, N, 700 + r))
+        s.xyz.copy_(dev(clouds[-1], cuda))
+        s.loss_pred.copy_(dev(rng.standard_normal((B, G)).astype(np.float32), cuda))
+        s.pred.copy_(dev((rng.standard_normal((s.P, k, 3)) * 0.08).astype(np.float32), cuda))
+        s.run()
+        torch.cuda.synchronize()
+        want.append({n: host(getattr(s, n)).copy() for n in ("fps_idx", "neighborhood", "mask", "per_patch", "total", "stats", "grad_pred")})
+        for n in want[-1]:
+            getattr(s, n).fill_(0)
+        steps.append(s)
+    ring = StepRing(steps).capture()
+    for _ in range(3):
+        ring.run()
+    torch.cuda.synchronize()
+    for s, w in zip(steps, want):
+        for n, v in w.items():
+            assert np.array_equal(host(getattr(s, n)), v), n
+    w0 = co.group(clouds[3], G, k)
+    assert np.array_equal(host(steps[3].fps_idx), w0["fps_idx"]) and np.array_equal(host(steps[3].neighborhood), w0["neighborhood"])
+
+
 # ------------------------------------------------------------------------------------------ SURVEY 8(f) rows
 @pytest.fixture(scope="module")
 def golden_next():
