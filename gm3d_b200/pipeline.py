@@ -22,6 +22,7 @@ import torch
 from . import _lib
 from .masking import mask_lengths
 
+FUSED_LANES_MAX_B = int(os.environ.get("GM3D_FUSED_LANES_MAX_B", "148"))  # tuning aid
 KERNELS_PER_STEP = 4  # unfused: fps, knn_group, hard_mask (+patch index), chamfer fused (fwd + bwd + loss reduction)
 FUSED_MAX_N, FUSED_MAX_G = 2048, 1024  # gm3d_cloud_step_f32 serves these; larger clouds use the 4-kernel sequence
 
@@ -186,7 +187,24 @@ class StepRing:
         n = len(self.steps)
         s0 = self.steps[0]
         nl = max(1, min(n, int(os.environ.get("GM3D_RING_LANES", "4"))))  # tuning aid; 1 = one stream
-        if not s0.fused and nl > 1:
+        if s0.fused and nl > 1 and 2 * s0.B <= FUSED_LANES_MAX_B and n >= 2 * nl:
+            # Small batches (one CTA per cloud fills a fraction of the 2 x 148 CTA slots): several chains of
+            # programmatic-dependent launches side by side, one per forked stream.
+            main = torch.cuda.current_stream(s0.dev)
+            if self._lanes is None or len(self._lanes) != nl:
+                self._lanes = [torch.cuda.Stream(s0.dev) for _ in range(nl)]
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for li, lane in enumerate(self._lanes):
+                lane.wait_event(fork)
+                mine = self.steps[li::nl]
+                with torch.cuda.stream(lane):
+                    for i, s in enumerate(mine):
+                        s.enqueue((_lib.STEP_OVERLAP_NEXT if i + 1 < len(mine) else 0) | (_lib.STEP_OVERLAP_PREV if i > 0 else 0))
+                join = torch.cuda.Event()
+                join.record(lane)
+                main.wait_event(join)
+        elif not s0.fused and nl > 1:
             # Kernel-sequence steps: the steps go round-robin to forked streams, so the FPS chain of one step -- G
             # dependent rounds, one CTA per cloud, issue slots half empty -- runs beside the kNN / Chamfer kernels of
             # another wherever SM resources allow (FPS CTAs of different steps pair up at N <= 2048; at N = 8192 the

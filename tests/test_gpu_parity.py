@@ -609,7 +609,7 @@ def test_step_ring_overlapped_steps_equal_serial_steps(cuda):
     B, N, G, k = 16, 1024, 64, 32
     rng = np.random.default_rng(9)
     steps, want = [], []
-    for r in range(6):
+    for r in range(9):  # >= 8 steps of a small batch: the ring runs them as four chains on forked streams
         s = GroupLossStep(B, N, G, k, 0.6, device=cuda, seed=4, rand_offset=r * B * G, fused=True)
         s.xyz.copy_(dev(synthetic_clouds(B, N, 300 + r), cuda))
         s.loss_pred.copy_(dev(rng.standard_normal((B, G)).astype(np.float32), cuda))
