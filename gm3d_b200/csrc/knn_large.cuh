@@ -18,9 +18,9 @@
 //   phase 2  a warp owns one query.  Its nchunks * 128 group keys are read as packed pairs: the packed minimum over
 //            a lane's words gives two minima of disjoint point sets per lane, 64 in all; their k-th smallest Tt
 //            proves that k points lie within Tt + |q|^2 + E, so only groups whose minimum is <= Tt + 2E can hold one
-//            of the k nearest -- about k groups.  They are compacted into a list and the warp evaluates FOUR listed
-//            groups per step with the reference expression (8 lanes each; the skewed ownership keeps the reads spread
-//            over the banks), appending `d <= Tt + |q|^2 + E` by ballot.  The <= 64 candidates are ordered exactly by
+//            of the k nearest -- about k groups.  They are compacted into a list and the warp evaluates EIGHT listed
+//            groups per step with the reference expression (8 lanes each, two independent chains per lane; the skewed
+//            ownership keeps the reads spread over the banks), appending `d <= Tt + |q|^2 + E` by ballot.  The <= 64 candidates are ordered exactly by
 //            order_candidates().  Anything unusual (more than 64 candidates or 128 groups: heavy ties, outliers that
 //            blow up E) takes the exact streaming selection instead.
 //

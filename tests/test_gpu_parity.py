@@ -55,6 +55,25 @@ def test_fps_bit_exact(cuda, kind, B, N, G):
     assert np.array_equal(host(ctr), np.take_along_axis(xyz, want[..., None].astype(np.int64), axis=1))
 
 
+def test_fps_two_stage_ties_and_ragged(cuda):
+    """4096 < N <= 8192 runs the two-stage arg-max (value first, index only in the warp(s) holding it): ragged N
+    (padding slots, non-bulk loader), clouds of few distinct points (every round ties across many warps, and G
+    exceeds the number of distinct points) and an all-identical cloud."""
+    from gm3d_b200 import ops
+    rng = np.random.default_rng(3)
+    base = synthetic_clouds(1, 50, 9, "ball")[0]
+    clouds = [
+        (synthetic_clouds(2, 5001, 21, "sphere"), 64),
+        (np.stack([base[rng.integers(0, 50, size=6000)] for _ in range(2)]), 300),
+        (np.full((1, 8192, 3), 0.25, dtype=np.float32), 40),
+        (synthetic_clouds(1, 4097, 5, "ball"), 4097),
+    ]
+    for xyz, G in clouds:
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        idx, _ = ops.fps_centers(dev(xyz, cuda), G)
+        assert np.array_equal(host(idx), co.fps(xyz, G))
+
+
 def test_fps_large_n_global_kernel(cuda):
     from gm3d_b200 import ops
     xyz = synthetic_clouds(2, 10000, 7, "ball")
