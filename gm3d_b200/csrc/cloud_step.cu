@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 12 ? 2 : 1) cloud_step_ke
                                     qy, qz, k, lane, cb);
 
         // gather + centre-normalise; lane l < k owns neighbour l
-        const unsigned pi = lane < k ? static_cast<unsigned>(top & 0xffffffffu) : 0u;
+        const unsigned pi = lane < k ? min(static_cast<unsigned>(top & 0xffffffffu), static_cast<unsigned>(N - 1)) : 0u;  // clamp: NaN inputs
         const float ox = sx[pi], oy = sy[pi], oz = sz[pi];
         const float bx = __fsub_rn(ox, qx), by = __fsub_rn(oy, qy), bz = __fsub_rn(oz, qz);
         const size_t row = (static_cast<size_t>(b) * G + g) * k;

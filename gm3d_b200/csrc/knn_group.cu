@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(kKnnThreads)
         if (!act[q]) continue;
         knn_finish<Q>(st, q, cbs + q * 64, lane);
         if (lane < k) {
-            const unsigned pi = static_cast<unsigned>(st.top[q] & 0xffffffffu);
+            // (clamp: only non-finite inputs can leave a sentinel in the list -- stay in bounds)
+            const unsigned pi = min(static_cast<unsigned>(st.top[q] & 0xffffffffu), static_cast<unsigned>(N - 1));
             const float d = key_dist(st.top[q]);
             const size_t o = (static_cast<size_t>(b) * G + g0 + q) * k + lane;
             if (idx_out) idx_out[o] = static_cast<int64_t>(pi);

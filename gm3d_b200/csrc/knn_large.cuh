@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kKlMaxThreads, 1) knn_large_kernel(const KnnLa
                     }
                 }
                 u64 top;
-                if (fast && total <= 64) {
+                if (fast && total <= 64 && total >= k) {  // total < k cannot happen for finite inputs (NaN coordinates)
                     float thr;
                     order_candidates(s_cloud, s_cloud + kKlChunk, s_cloud + 2 * kKlChunk, 0, total, make_float2(qv.x, qv.x),
                                      make_float2(qv.y, qv.y), make_float2(qv.z, qv.z), k, lane, cb, top, thr);
@@ -299,7 +299,8 @@ __global__ void __launch_bounds__(kKlMaxThreads, 1) knn_large_kernel(const KnnLa
                     __syncwarp();
                 }
                 if (lane < k) {
-                    const unsigned pi = static_cast<unsigned>(top & 0xffffffffu);
+                    // (the clamp only matters for non-finite inputs, where the list can hold sentinels: stay in bounds)
+                    const unsigned pi = min(static_cast<unsigned>(top & 0xffffffffu), static_cast<unsigned>(N - 1));
                     const size_t o = (static_cast<size_t>(b) * G + q0 + qi) * k + lane;
                     if (p.idx_out) p.idx_out[o] = static_cast<int64_t>(pi);
                     if (p.dist_out) p.dist_out[o] = __fsqrt_rn(key_dist(top));

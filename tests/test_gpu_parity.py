@@ -210,6 +210,24 @@ def test_knn_large_heavy_ties(cuda):
     assert (host(I)[0] == np.arange(9)[None]).all()
 
 
+@pytest.mark.parametrize("N", [800, 1500, 9000])
+def test_knn_nonfinite_inputs_stay_in_bounds(cuda, N):
+    """NaN / inf coordinates make the result meaningless (as upstream), but every kernel must stay in bounds: indices in
+    [0, N), no CUDA error, and the clouds of the batch without bad points are still exact."""
+    from gm3d_b200.knn import KNN
+    xyz = synthetic_clouds(3, N, 31, "ball")
+    q = xyz[:, :40].copy()
+    bad = xyz.copy()
+    bad[1, 5::97] = np.nan
+    bad[1, 7::131, 1] = np.inf
+    D, I = KNN(32, True)(dev(bad, cuda), dev(q, cuda))
+    torch.cuda.synchronize()
+    Ih = host(I)
+    assert Ih.min() >= 0 and Ih.max() < N
+    _, Iw = co.knn(xyz, q, 32)
+    assert np.array_equal(Ih[0], Iw[0]) and np.array_equal(Ih[2], Iw[2])
+
+
 # ------------------------------------------------------------------------------------------ Group
 @pytest.mark.parametrize("tag", ["c1", "m2ae_l2", "ragged", "g_eq_n"])
 def test_group_matches_reference_golden(cuda, golden, tag):
