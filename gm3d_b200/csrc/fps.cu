@@ -28,7 +28,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 // per-thread arg-max tournament (3 ALU-pipe instructions per point in every warp) is gone, at the price of a
 // second barrier per round.
 template <int THREADS, int PPT, bool TWO_STAGE = false>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, THREADS <= 256 ? 4 : 1)  // <= 256 threads: at most 64 registers, so a CTA fits beside other kernels
     fps_reg_kernel(const float* __restrict__ xyz, int N, int G, int32_t* __restrict__ idx,
                    float* __restrict__ centers, int use_bulk) {
     constexpr int NWARPS = THREADS / 32;

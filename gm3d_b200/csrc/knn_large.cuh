@@ -66,7 +66,9 @@ struct KnnLargeParams {
 };
 
 __device__ __forceinline__ void group_bar(int grp, int group_threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(group_threads) : "memory");
+    // literal barrier ids: with a register id ptxas reserves all 16 barriers of the SM and no other CTA can be resident
+    if (grp == 0) asm volatile("bar.sync 1, %0;" ::"r"(group_threads) : "memory");
+    else asm volatile("bar.sync 2, %0;" ::"r"(group_threads) : "memory");
 }
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
     float r;
