@@ -35,10 +35,11 @@ class GroupLossStep:
         can_fuse = N <= FUSED_MAX_N and G <= FUSED_MAX_G and k <= _lib.KNN_MAX_K
         if fused and not can_fuse:
             raise NotImplementedError(f"gm3d_cloud_step_f32 serves N <= {FUSED_MAX_N}, G <= {FUSED_MAX_G}")
-        # default: one CTA per cloud pays off when a cloud's selection work fits beside its FPS chain (measured on
-        # B200: C1, C2, C4, M2AE levels 1-2 yes -- small batches included, because overlapped steps share the
-        # GPU; M2AE level 0 with G=512 x 2 tiles no)
-        worth = G * ((N + 1023) // 1024) <= 256
+        # default: one CTA per cloud pays off while the FPS chain (G dependent rounds, ~0.3 us each beside the workers)
+        # is not what the CTA waits for.  Measured on B200 against the kernel sequence spread over forked streams:
+        # C1, C2, C4, M2AE level 2 (G <= 128) fused; M2AE level 1 (G = 256: 78 us fused, 62 us as a sequence) and
+        # level 0 (G = 512) as a sequence.
+        worth = G <= 128
         if fused is None and os.environ.get("GM3D_STEP_FUSED") in ("0", "1"):  # tuning aid (A/B runs of the two paths)
             fused = os.environ["GM3D_STEP_FUSED"] == "1" and can_fuse
         self.fused = (can_fuse and worth) if fused is None else fused
