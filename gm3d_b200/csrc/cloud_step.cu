@@ -115,7 +115,7 @@ template <int FW, int PPT, int WARPS, bool LOSS>
 __global__ void __launch_bounds__(WARPS * 32, WARPS <= 12 ? 2 : 1) cloud_step_kernel(const __grid_constant__ CloudStepParams p) {
     constexpr int kCsFpsWarps = FW, kCsFpsThreads = FW * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int2 s_red[2][kCsMaxFpsWarps];
+    __shared__ __align__(128) int2 s_red[2][kCsMaxFpsWarps];  // 2 x 64 bytes: the round's buffer is an XOR of the address
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_mask_ready;  // 1 once s_msel / s_mrank are valid
     __shared__ int s_next;        // next patch id to hand out (patches are claimed in the order their centres appear)
@@ -201,7 +201,12 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 12 ? 2 : 1) cloud_step_ke
         // ---------------- sampler warps: G - 1 dependent rounds
         int old = 0;
         const int rounds = p.dbg_mode == 3 ? 1 : G;
-        const int2* red_rd = &s_red[0][lane & (FW - 1)];  // every lane re-reduces the FW warp results (duplicates are harmless)
+        // The per-warp results go through shared memory by explicit 32-bit addresses, toggled between the two buffers
+        // with an XOR: left to the compiler, the generic-to-shared conversion (S2UR + LEA glue, ~15 instructions and two
+        // long-latency special-register reads) was redone on the chain's critical path every round.
+        static_assert(sizeof(int2) * kCsMaxFpsWarps == 64, "s_red buffer toggle");
+        uint32_t red_wr = smem_u32(&s_red[1][warp]);                 // round j = 1 uses buffer 1
+        uint32_t red_rd = smem_u32(&s_red[1][lane & (FW - 1)]);      // every lane re-reduces the FW warp results (duplicates are harmless)
         for (int j = 1; j < rounds; ++j) {
             const float* w = s_aos + 3 * old;  // winner of the previous round (AoS copy: one address, three loads)
             const float x1 = w[0], y1 = w[1], z1 = w[2];
@@ -231,9 +236,11 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 12 ? 2 : 1) cloud_step_ke
             const int besti = mi[0] * kCsFpsThreads + ftid;
             const int vmax = __reduce_max_sync(kFull, v);
             const int kmin = __reduce_min_sync(kFull, v == vmax ? besti : INT_MAX);
-            if (lane == 0) s_red[j & 1][warp] = make_int2(vmax, kmin);
+            if (lane == 0) asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(red_wr), "r"(vmax), "r"(kmin) : "memory");
             fps_bar<kCsFpsThreads>();
-            const int2 r = red_rd[(j & 1) * kCsMaxFpsWarps];
+            int2 r;
+            asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(red_rd) : "memory");
+            red_wr ^= 64u, red_rd ^= 64u;
             const int gmax = __reduce_max_sync(kFull, r.x);
             old = __reduce_min_sync(kFull, r.x == gmax ? r.y : INT_MAX);
             if (ftid == 0) {  // publish centre j: the arrive releases the store, a worker's wait acquires it
