@@ -52,6 +52,13 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
 __device__ __forceinline__ float2 sumsq_acc2(float2 a, float2 b, float2 c) { return fma2(c, c, fma2(b, b, mul2(a, a))); }
 __device__ __forceinline__ float2 sumsq_nvcc2(float2 a, float2 b, float2 c) { return fma2(c, c, fma2(a, a, mul2(b, b))); }
 
+// 3-input minimum (sm_100 FMNMX3): costs one ALU-pipe slot like the 2-input form (tools/ubench/fp32_pipes.cu)
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 // Order-preserving view of a float as a signed int for values in {-1} U [0, +inf]: non-negative floats

@@ -70,11 +70,6 @@ __device__ __forceinline__ void group_bar(int grp, int group_threads) {
     if (grp == 0) asm volatile("bar.sync 1, %0;" ::"r"(group_threads) : "memory");
     else asm volatile("bar.sync 2, %0;" ::"r"(group_threads) : "memory");
 }
-__device__ __forceinline__ float fmin3(float a, float b, float c) {
-    float r;
-    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-    return r;
-}
 // order-preserving unsigned key of a float (any sign) and its inverse
 __device__ __forceinline__ unsigned okey(float f) {
     const unsigned b = __float_as_uint(f);

@@ -227,11 +227,11 @@ __device__ __forceinline__ bool bootstrap_query(const float* __restrict__ sx, co
                                       sub2(make_float2(z.z, z.w), q2z));
         d[blk * 4 + 0] = d01.x, d[blk * 4 + 1] = d01.y, d[blk * 4 + 2] = d23.x, d[blk * 4 + 3] = d23.y;
         if (blk & 1) {
-            mb = fminf(fminf(mb, d01.x), d01.y);
-            mb = fminf(fminf(mb, d23.x), d23.y);
+            mb = fmin3(mb, d01.x, d01.y);
+            mb = fmin3(mb, d23.x, d23.y);
         } else {
-            ma = fminf(fminf(ma, d01.x), d01.y);
-            ma = fminf(fminf(ma, d23.x), d23.y);
+            ma = fmin3(ma, d01.x, d01.y);
+            ma = fmin3(ma, d23.x, d23.y);
         }
     }
     // T = an upper bound of the k-th smallest of the 64 group minima.  Only a bound is needed, so the minima are
@@ -337,7 +337,7 @@ __device__ __forceinline__ void stream_tile(KnnStream<Q>& s, const float* __rest
                                 sub2(make_float2(z.x, z.y), q2z));
             d23[q] = sumsq_acc2(sub2(make_float2(x.z, x.w), q2x), sub2(make_float2(y.z, y.w), q2y),
                                 sub2(make_float2(z.z, z.w), q2z));
-            const float m = fminf(fminf(fminf(d01[q].x, d01[q].y), d23[q].x), d23[q].y);
+            const float m = fmin3(fminf(d01[q].x, d01[q].y), d23[q].x, d23[q].y);
             any = any || m <= s.thr[q];
         }
         if (!__any_sync(kFull, any)) continue;
