@@ -49,6 +49,9 @@ def _stale(out: str, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
+    extra = os.environ.get("GM3D_NVCC_FLAGS", "").split()  # e.g. -DGM3D_CS_DEBUG (tuning aids of the fused kernel)
+    flags = NVCC_FLAGS + extra
+    force = force or bool(extra)
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(ROOT, "include", "gm3d.h"))
@@ -61,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, *flags, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, r
 

@@ -145,7 +145,15 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 12 ? 2 : 1) cloud_step_ke
     const bool is_mask_warp = LOSS && warp == WARPS - 1;
     const float* cloud = p.xyz + static_cast<size_t>(b) * N * 3;
     const int M = G - p.len_keep;
+    // Tuning aids (GM3D_CS_MODE, GM3D_CS_TRACE) are compiled in only with -DGM3D_CS_DEBUG: even untaken, their branches
+    // and live values cost the production kernel 1.5 % (measured).
+#ifdef GM3D_CS_DEBUG
     unsigned long long* tr = p.trace ? p.trace + static_cast<size_t>(b) * 64 : nullptr;
+    const int dbg_mode = p.dbg_mode;
+#else
+    constexpr unsigned long long* tr = nullptr;
+    constexpr int dbg_mode = 0;
+#endif
     if (tr && tid == 0) {
         unsigned long long gt;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
@@ -200,7 +208,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 12 ? 2 : 1) cloud_step_ke
     if (is_fps) {
         // ---------------- sampler warps: G - 1 dependent rounds
         int old = 0;
-        const int rounds = p.dbg_mode == 3 ? 1 : G;
+        const int rounds = dbg_mode == 3 ? 1 : G;
         // The per-warp results go through shared memory by explicit 32-bit addresses, toggled between the two buffers
         // with an XOR: left to the compiler, the generic-to-shared conversion (S2UR + LEA glue, ~15 instructions and two
         // long-latency special-register reads) was redone on the chain's critical path every round.
@@ -318,7 +326,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 12 ? 2 : 1) cloud_step_ke
             float* o = p.nbhd + (row + lane) * 3;
             o[0] = bx, o[1] = by, o[2] = bz;
         }
-        if (LOSS && p.dbg_mode != 2) {
+        if (LOSS && dbg_mode != 2) {
             while (ld_volatile_s32(&s_mask_ready) == 0) __nanosleep(64);
             const int mr = s_mrank[g];
             if (mr >= 0) {  // warp-uniform: patch g is masked, its prediction is row b*M + mr
@@ -339,7 +347,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 12 ? 2 : 1) cloud_step_ke
             }
         }
     };
-    if (p.dbg_mode != 1 && p.dbg_mode != 3) {
+    if (dbg_mode != 1 && dbg_mode != 3) {
         if constexpr (DYNAMIC) {
             for (;;) {
                 int g = 0;

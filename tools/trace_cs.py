@@ -1,5 +1,8 @@
 """Per-CTA timeline of the fused kernel (clock64 stamps written when GM3D_CS_TRACE is set).
 
+Needs the tuning aids compiled in:  GM3D_NVCC_FLAGS=-DGM3D_CS_DEBUG python -m gm3d_b200.build  (rebuild without
+the flag afterwards: the production kernel leaves them out).
+
     python tools/trace_cs.py [--config c2]
 """
 import argparse
