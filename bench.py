@@ -94,6 +94,31 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------------ shared config
+def buffer_set_bytes(B, N, G, k, M):
+    """Bytes of one step's buffer set (inputs + every output), from the shapes alone (both arms print it)."""
+    P = B * M
+    return (B * N * 3 * 4 + P * k * 3 * 4 + B * G * 4                      # xyz, pred, loss_pred
+            + B * G * 4 + B * G * 3 * 4 + B * G * k * 3 * 4                # fps_idx, centres, neighbourhood
+            + B * G + P * 4                                                # mask, patch_index
+            + 2 * P * k * 4 + 2 * P * k * 4 + P * 4 + P * k * 3 * 4)       # dist1/2, idx1/2, per_patch, grad_pred
+
+
+def ring_size(B, N, G, k, M):
+    return int(min(64, max(4, -(-2 * L2_BYTES // buffer_set_bytes(B, N, G, k, M)))))
+
+
+def config_dict(cfg):
+    """The workload description both arms print (identical keys and values => the driver's same_config check)."""
+    from gm3d_b200.masking import mask_lengths
+    B, N, G, k, ratio, desc = cfg
+    len_keep, _ = mask_lengths(G, ratio, 199, 400)
+    M = G - len_keep
+    ring = ring_size(B, N, G, k, M)
+    return {"workload": desc, "B_per_gpu": B, "N": N, "G": G, "k": k, "M": M,
+            "l2_policy": f"inputs larger than L2: ring of {ring} buffer sets x {buffer_set_bytes(B, N, G, k, M) / 1e6:.1f} MB"}
+
+
 # ------------------------------------------------------------------------------------------ reference arm
 def cpu_step(co, x, loss_pred, pred, G, k, len_keep, len_loss, rand_keys):
     """The same step with the CPU oracle (reference operator semantics)."""
@@ -142,12 +167,11 @@ def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B, N, G, k, ratio, desc = cfg
     base, ms = time_cpu(cfg, budget_s=150.0, steps=args.steps, warmup=max(1, min(args.warmup, 3)))
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "clouds/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "B_per_gpu": B, "N": N, "G": G, "k": k},
+            "config": config_dict(cfg),
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -155,13 +179,63 @@ def run_reference(args, cfg):
 
 
 # ------------------------------------------------------------------------------------------ native arm
+_STAGE = ["start"]
+
+
 def _stage(msg):
-    if os.environ.get("GM3D_BENCH_TRACE"):
+    _STAGE[0] = msg
+    if os.environ.get("GM3D_BENCH_TRACE") or int(os.environ.get("WORLD_SIZE", "1")) > 1:
         sys.stderr.write(f"[bench r{os.environ.get('RANK', '0')} {time.time() % 1000:8.3f}] {msg}\n")
         sys.stderr.flush()
 
 
+def _watchdog(seconds: float):
+    """A hung collective must end the run with a rank-tagged stage, not occupy the box until the driver kills it."""
+    import faulthandler
+
+    def fire():
+        sys.stderr.write(f"[bench r{os.environ.get('RANK', '0')}] WATCHDOG after {seconds:.0f} s in stage '{_STAGE[0]}'\n")
+        faulthandler.dump_traceback(file=sys.stderr)
+        sys.stderr.flush()
+        os._exit(3)
+
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
+def oracle_check_step(s, x, lp, pred):
+    """Compare one ring slot (its buffers as the timed launches left them) with the CPU oracle: indices, mask and
+    arg-mins bit-exact, losses / gradients within 1e-5 relative.  Returns 'ok' or raises AssertionError."""
+    from oracle import c_oracle as co
+    w = co.group(x, s.G, s.k)
+    assert np.array_equal(s.fps_idx.cpu().numpy(), w["fps_idx"]), "fps_idx"
+    assert np.array_equal(s.center.cpu().numpy(), w["center"]), "center"
+    assert np.array_equal(s.neighborhood.cpu().numpy(), w["neighborhood"]), "neighborhood"
+    mask = s.mask.cpu().numpy()
+    assert (mask.sum(1) == s.M).all(), "mask cardinality"
+    if s.len_loss > 0:
+        order = np.argsort(lp, axis=1, kind="stable")[:, s.G - s.len_loss:]
+        assert (np.take_along_axis(mask, order, axis=1) == 1).all(), "mask misses a top-loss patch"
+    assert np.array_equal(s.patch_index.cpu().numpy(), np.flatnonzero(mask.reshape(-1))), "patch_index"
+    gt = w["neighborhood"][mask.astype(bool)]
+    d1, d2, i1, i2 = co.chamfer_fwd(pred, gt)
+    assert np.array_equal(s.dist1.cpu().numpy(), d1) and np.array_equal(s.dist2.cpu().numpy(), d2), "chamfer dist"
+    assert np.array_equal(s.idx1.cpu().numpy(), i1) and np.array_equal(s.idx2.cpu().numpy(), i2), "chamfer idx"
+    pp = co.chamfer_per_patch(d1, d2, 2)
+    assert np.allclose(s.per_patch.cpu().numpy(), pp, rtol=1e-5, atol=0), "per_patch"
+    assert abs(s.total.item() - pp.mean()) <= 1e-5 * abs(pp.mean()), "total"
+    g = np.full((s.P, s.k), 1.0 / (s.P * s.k), dtype=np.float32)
+    ga, _ = co.chamfer_bwd(pred, gt, i1, i2, g, g)
+    got = s.grad_pred.cpu().numpy()
+    assert np.abs(got - ga).max() <= 1e-5 * np.abs(ga).max(), "grad_pred"
+    return "ok"
+
+
 def run_native(args, cfg):
+    import datetime
+
     import torch
     import torch.distributed as dist
 
@@ -177,45 +251,61 @@ def run_native(args, cfg):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    wd = _watchdog(float(os.environ.get("GM3D_BENCH_WATCHDOG_S", "540")))
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # a mismatched / missing collective aborts within the timeout instead of spinning in NCCL kernels
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "1")
+        os.environ.setdefault("TORCH_NCCL_ENABLE_MONITORING", "1")
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     B, N, G, k, ratio, desc = cfg
     K, W = args.steps, max(args.warmup, 3)
+    cdict = config_dict(cfg)
+    M = cdict["M"]
+    ring = ring_size(B, N, G, k, M)
+
+    # ---- collective mode: the per-step statistics all-reduce
+    inbox = None
+    mode = "none"
+    if world > 1:
+        mode = args.collective
+        if mode in ("auto", "peer"):
+            from gm3d_b200.dist import PeerInbox
+            try:
+                inbox = PeerInbox(ring)
+                mode = "peer"
+            except (RuntimeError, NotImplementedError) as e:  # raised on every rank together
+                _stage(f"peer memory unavailable ({e}); falling back to NCCL")
+                if args.collective == "peer":
+                    raise
+                mode = "nccl"
+    collective = {"none": "none",
+                  "peer": "per step, inside the loss launch: {sum, sum_sq, count} pushed to every rank's inbox over "
+                          "NVLink peer memory and summed in rank order (gm3d_step_reduce_t)",
+                  "nccl": "one NCCL all-reduce of the packed (steps, 4) statistics per graph of steps"}[mode]
 
     # ring of buffer sets larger than L2 so every step reads cold inputs and writes cold outputs
-    probe = GroupLossStep(B, N, G, k, ratio, device=dev)
-    per_set = sum({t.untyped_storage().data_ptr(): t.untyped_storage().nbytes()
-                   for t in vars(probe).values() if isinstance(t, torch.Tensor)}.values())  # views share storage
-    ring = int(min(64, max(4, -(-2 * L2_BYTES // per_set))))
-    M = probe.M
-    del probe
-
-    steps = []
+    steps, inputs = [], []
     for r in range(ring):
         s = GroupLossStep(B, N, G, k, ratio, device=dev, seed=1234, rand_offset=(rank * ring + r) * B * G)
         x, lp, pred = synthetic_batch(B, N, G, k, M, 1234 + 1000 * rank + r)
         s.xyz.copy_(torch.from_numpy(x)); s.loss_pred.copy_(torch.from_numpy(lp)); s.pred.copy_(torch.from_numpy(pred))
         steps.append(s)
+        inputs.append((x, lp, pred) if r == 0 else None)
 
     # K timed steps = q replays of the whole ring captured as ONE graph + one graph of the first K % ring steps.
-    # The steps of a ring share no buffer, so inside a graph the fused kernels are chained by programmatic
-    # dependent launch; with N > 1 each graph ends with ONE all-reduce of its steps' [sum, sum_sq, count].
-    # --no-overlap: one graph per step (kernel after kernel, one all-reduce per step).
+    # --no-overlap: one graph per step (kernel after kernel).
     overlap = not args.no_overlap
-    collective = "none"
     chunks = {}
 
     def chunk(n):
         if n not in chunks:
             if overlap:
-                chunks[n] = StepRing(steps[:n], reduce_stats=world > 1).capture()
+                chunks[n] = StepRing(steps[:n], reduce=mode, inbox=inbox).capture()
             else:
-                chunks[n] = [steps[i].capture((lambda s=steps[i]: dist.all_reduce(s.stats[:3])) if world > 1 else None)
-                             if steps[i].graph is None else steps[i] for i in range(n)]
+                rings = [StepRing([steps[i]], reduce=mode, inbox=_Slot(inbox, i) if inbox is not None else None).capture()
+                         for i in range(n)]
+                chunks[n] = rings
         return chunks[n]
-
-    if world > 1:
-        collective = "one NCCL all-reduce per graph of steps" if overlap else "one NCCL all-reduce per step, in-graph"
 
     def run_chunk(n):
         c = chunk(n)
@@ -231,6 +321,14 @@ def run_native(args, cfg):
         if n % ring:
             run_chunk(n % ring)
 
+    align = torch.zeros(1, device=dev)
+
+    def device_align():
+        # device-side start alignment: an all-reduce ENQUEUED on the stream completes on all ranks within a few us of
+        # each other, so the ranks enter a timed region together without a host round trip
+        if world > 1:
+            dist.all_reduce(align)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -245,34 +343,75 @@ def run_native(args, cfg):
     run_steps(max(W, ring))  # at least one pass over every buffer set
     run_steps(K)             # and one pass over exactly the graphs that are timed
     barrier()
+    # ---- how many repetitions of the K-step region: identical on every rank (derived from an all-reduced estimate)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    device_align()
+    e0.record()
+    run_steps(K)
+    e1.record()
+    torch.cuda.synchronize()
+    est = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    est_ms = max(est.item(), 1e-3)
+    R = args.reps if args.reps > 0 else int(min(3000, max(25, -(-args.min_region_ms // est_ms))))
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
         time.sleep(0.15)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    _stage("timed region")
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(R)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(R)]
+    _stage(f"timed region: {R} repetitions of {K} steps")
     barrier()
-    ev0.record()
-    run_steps(K)
-    ev1.record()
+    for r in range(R):
+        device_align()
+        ev0[r].record()
+        run_steps(K)
+        ev1[r].record()
     barrier()
-    ms = ev0.elapsed_time(ev1)
-    # keep the GPU busy a little longer so nvidia-smi gets samples under load for short runs
-    t_end = time.time() + 0.4
-    while time.time() < t_end:
-        run_steps(ring)
-        torch.cuda.synchronize()
     clk = clocks.stop() if rank == 0 else None
+    times = torch.tensor([ev0[r].elapsed_time(ev1[r]) for r in range(R)], device=dev)
     if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)  # per repetition: the slowest rank
+    tl = np.sort(times.cpu().numpy())
+    ms = float(np.median(tl))
     value = world * B * K / (ms * 1e-3)
-
     _stage("timed region done")
+
+    # ---- checks on what the timed launches left behind
+    parity = allreduce = None
+    if rank == 0 and not args.no_checks:
+        try:
+            parity = oracle_check_step(steps[0], *inputs[0])
+        except AssertionError as e:
+            parity = f"FAILED: {e}"
+    if world > 1 and not args.no_checks:
+        # every rank's own [sum, sum_sq, count] of the ring's steps, gathered; head must be their sum over the ranks
+        c = chunk(ring)
+        rings = [c] if overlap else c
+        mine = torch.stack([s.stats[:3] for s in steps]).contiguous()
+        allv = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        want = allv[0].clone()
+        for q in range(1, world):
+            want = want + allv[q]  # rank order, fp32: the order the peer reduction uses
+        head = torch.cat([r_.head for r_ in rings])
+        got = head[:, :3]
+        if mode == "none":
+            ok, ranks_ok = torch.equal(got, mine), True
+        else:  # peer: summed in rank order => bit-identical; NCCL: its own (deterministic) order
+            ok = torch.equal(got, want) if mode == "peer" else torch.allclose(got, want, rtol=1e-6, atol=0)
+            ranks_ok = bool((head[:, 3] == world).all())  # column 3 counts the ranks summed
+        st_ok = inbox is None or int(inbox.status.item()) == 0
+        flag = torch.tensor([1.0 if (ok and ranks_ok and st_ok) else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        allreduce = "ok" if flag.item() == 1.0 else "FAILED: head != sum over ranks of the per-rank statistics"
+
     # ---- per-kernel device times (CUDA events on the launching stream, same ring => cold L2)
     per_kernel = {}
+    single = None
     if rank == 0:
+        _stage("per-kernel times")
         L = steps[0].lib
         p = lambda t: t.data_ptr()  # noqa: E731
         g = 1.0 / (steps[0].P * k)
@@ -281,20 +420,23 @@ def run_native(args, cfg):
             "knn_group": lambda s, st: _knn_group_only(L, s, st),
             "chamfer_fused": lambda s, st: L.gm3d_chamfer_fused_f32(
                 p(s.pred), p(s.neighborhood), p(s.patch_index), s.P, k, k, g, g, p(s.dist1), p(s.dist2), p(s.idx1),
-                p(s.idx2), p(s.per_patch), p(s.total), p(s.stats), 2, p(s.grad_pred), None, p(s.cd_ws), st),
+                p(s.idx2), p(s.per_patch), p(s.total), p(s.stats), 2, p(s.grad_pred), None, None, 0, p(s.cd_ws), st),
             "chamfer_fwd": lambda s, st: L.gm3d_chamfer_fwd_f32(p(s.pred), p(s.neighborhood), p(s.patch_index), s.P, k, k,
                                                             p(s.dist1), p(s.dist2), p(s.idx1), p(s.idx2), p(s.per_patch),
                                                             None, None, 2, None, st),
             "chamfer_bwd": lambda s, st: L.gm3d_chamfer_bwd_f32(p(s.pred), p(s.neighborhood), p(s.patch_index), p(s.idx1),
                                                             p(s.idx2), None, None, g, g, s.P, k, k, p(s.grad_pred), None, st),
             "hard_mask": lambda s, st: L.gm3d_hard_mask_f32(p(s.loss_pred), B, G, s.len_keep, s.len_loss, None, 1, 0,
-                                                        p(s.mask), p(s.patch_index), st),
+                                                        p(s.mask), p(s.patch_index), 0, st),
         }
-        if steps[0].fused:
+        if steps[0].group_per_cloud:
+            launchers["group"] = lambda s, st: L.gm3d_cloud_step_f32(
+                p(s.xyz), B, N, G, k, p(s.fps_idx), p(s.center), None, p(s.neighborhood), None, None, 0, 0, None, 0, 0,
+                None, None, None, 0.0, 0.0, 2, None, None, None, None, None, None, None, None, 0, None, None, st)
             launchers["cloud_step"] = lambda s, st: L.gm3d_cloud_step_f32(
                 p(s.xyz), B, N, G, k, p(s.fps_idx), p(s.center), None, p(s.neighborhood), None, p(s.loss_pred), s.len_keep,
                 s.len_loss, None, s.seed, s.rand_offset, p(s.mask), p(s.patch_index), p(s.pred), g, g, 2, p(s.dist1),
-                p(s.dist2), p(s.idx1), p(s.idx2), p(s.per_patch), p(s.total), p(s.stats), p(s.grad_pred), 0, p(s.cd_ws), st)
+                p(s.dist2), p(s.idx1), p(s.idx2), p(s.per_patch), p(s.total), p(s.stats), p(s.grad_pred), 0, None, p(s.cd_ws), st)
         for name, fn in launchers.items():
             # one graph holding `ring` launches of this kernel (one per buffer set => cold L2 every launch);
             # replayed so that host launch gaps do not pollute the per-launch time
@@ -321,6 +463,32 @@ def run_native(args, cfg):
             b.record()
             torch.cuda.synchronize()
             per_kernel[name] = a.elapsed_time(b) * 1e3 / (reps * ring)  # us per launch, back-to-back in a graph
+
+        # ---- the same work as ONE launch per step (gm3d_cloud_step_f32 with pred): reported, not the headline
+        if steps[0].group_per_cloud:
+            _stage("single-launch ring")
+            one = []
+            for r in range(ring):
+                s = GroupLossStep(B, N, G, k, ratio, device=dev, seed=1234, rand_offset=r * B * G, path="single")
+                s.in_arena.copy_(steps[r].in_arena)
+                one.append(s)
+            sr = StepRing(one).capture()
+            for _ in range(3):
+                sr.run()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(25):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                sr.run()
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            t1 = float(np.median(ts)) / ring
+            single = {"value": B / (t1 * 1e-3), "unit": "clouds/s", "ms_per_step": t1, "kernels_per_step": 1,
+                      "note": "gm3d_cloud_step_f32 with pred: usable only when pred does not depend on this step's "
+                              "grouping / mask; one GPU, this rank's share"}
+            del sr, one
 
     _stage("e2e")
     # ---- end-to-end: every step fed from pinned host memory, results read back
@@ -375,18 +543,18 @@ def run_native(args, cfg):
     dt_cloud, hs1 = time_e2e(True)
     hs = [hs0]
     if world > 1:
-        t = torch.tensor([dt], device=dev)
+        t = torch.tensor([dt, dt_cloud], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = t.item()
+        dt, dt_cloud = t[0].item(), t[1].item()
     e2e = {"value": world * B * Ke / dt, "unit": "clouds/s", "h2d_bytes_per_step": hs[0].h2d_bytes,
            "d2h_bytes_per_step": hs[0].d2h_bytes, "ms_per_step": dt / Ke * 1e3, "steps": Ke,
            "pcie_gbs": (hs[0].h2d_bytes + hs[0].d2h_bytes) * Ke / dt / 1e9,
            "losses_read": n_read,
            "cloud_only": {"value": world * B * Ke / dt_cloud, "unit": "clouds/s", "h2d_bytes_per_step": hs1.h2d_bytes,
                           "note": "only the point clouds cross PCIe; pred / loss_pred stay on the device, where the reference's "
-                                  "decoder and loss predictor produce them (per rank, not max-reduced)"},
-           "how": f"{NGROUP} graphs in flight on {NGROUP} streams, each {SUB} x [1 H2D copy from pinned memory, the step, "
-                  "1 D2H copy]; every step's loss read on the host; wall clock, max over ranks"}
+                                  "decoder and loss predictor produce them"},
+           "how": f"{NGROUP} graphs in flight on {NGROUP} streams, each {SUB} x [1 H2D copy from pinned memory, the step "
+                  f"({steps[0].kernels_per_step} launches), 1 D2H copy]; every step's loss read on the host; wall clock, max over ranks"}
 
     _stage("e2e done")
     if rank == 0:
@@ -399,26 +567,37 @@ def run_native(args, cfg):
         hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
         fp32_peak = 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12  # TFLOP/s, non-tensor FP32
         bpc = steps[0].bytes_per_cloud()
-        evals = {"fps": (G - 1) * N, "knn_group": G * N, "chamfer_fused": 2 * M * k * k, "chamfer_fwd": 2 * M * k * k,
-                 "cloud_step": (G - 1) * N + G * N + M * k * k}
-        traffic = {}
-        try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        evals = {"fps": (G - 1) * N, "knn_group": G * N, "group": (G - 1) * N + G * N, "chamfer_fused": M * k * k,
+                 "chamfer_fwd": M * k * k, "cloud_step": (G - 1) * N + G * N + M * k * k}
+        ncu = {}
+        try:  # per-launch figures of the committed ncu --set full capture of the timed kernels (profiles/)
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                traffic = json.load(f).get(args.config, {})
+                ncu = json.load(f).get(args.config, {})
         except (OSError, ValueError):
             pass
-        if steps[0].fused:
-            # the step IS one kernel: its average duration over the timed region is the step time (launches
-            # overlap tail-to-head under programmatic dependent launch); the isolated launch is in roofline_detail
-            dom, dom_us = "cloud_step", ms / K * 1e3
+        us_step = ms / K * 1e3
+        if steps[0].group_per_cloud:
+            # the group launches chain back to back on their stream (the mask / loss launches run beside them on forked
+            # streams), so over the timed region the average duration of a group launch on its stream IS the step time
+            dom, dom_us = "group", us_step
         else:
-            dom = max((n for n in per_kernel if n in bpc), key=lambda n: per_kernel[n])
+            dom = max((n for n in per_kernel if n in bpc and n not in ("cloud_step", "group")), key=lambda n: per_kernel[n])
             dom_us = per_kernel[dom]
-        ach = bpc[dom] * B / (dom_us * 1e-6) / 1e9
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": traffic.get(dom), "peak_source": peak_src,
-                    "us_per_launch": dom_us, "algorithmic_bytes_per_launch": bpc[dom] * B,
-                    "note": "latency/issue-bound at this size: one CTA per cloud, 63 dependent FPS rounds; see DESIGN.md"}
+        hbm_gbs = bpc[dom] * B / (dom_us * 1e-6) / 1e9
+        fp32_tf = 8 * evals.get(dom, 0) * B / (dom_us * 1e-6) / 1e12
+        hbm_frac, fp32_frac = hbm_gbs / hbm_peak, fp32_tf / fp32_peak
+        nk = ncu.get(dom) if isinstance(ncu.get(dom), dict) else {}
+        by_fp32 = fp32_frac > hbm_frac  # the roof the kernel sits closest to (min(HBM, FP32))
+        roofline = {"kernel": dom, "bound": "fp32" if by_fp32 else "hbm",
+                    "achieved": fp32_tf if by_fp32 else hbm_gbs, "peak": fp32_peak if by_fp32 else hbm_peak,
+                    "unit": "TFLOP/s" if by_fp32 else "GB/s", "frac": fp32_frac if by_fp32 else hbm_frac,
+                    "traffic": nk.get("dram_bytes"), "peak_source": peak_src if not by_fp32 else "148 SM x 128 lanes x 2 x max SM clock (non-tensor FP32)",
+                    "hbm_gbs": hbm_gbs, "hbm_peak": hbm_peak, "hbm_frac": hbm_frac,
+                    "fp32_tflops": fp32_tf, "fp32_peak": fp32_peak, "fp32_frac": fp32_frac,
+                    "issue_slot_frac": nk.get("issue_slot_frac"), "us_per_launch": dom_us,
+                    "algorithmic_bytes_per_launch": bpc[dom] * B, "algorithmic_flop_per_launch": 8 * evals.get(dom, 0) * B,
+                    "limiter": "instruction issue + the dependent latency of the G-round sampling chain (one CTA per cloud); "
+                               "neither roof binds -- see DESIGN.md 4.1"}
         detail = {}
         for n, us in per_kernel.items():
             d = {"us_per_launch": round(us, 3)}
@@ -431,33 +610,55 @@ def run_native(args, cfg):
             if n == "fps":
                 d["us_per_iteration"] = round(us / max(G - 1, 1), 4)
             detail[n] = d
-        step_bytes = (bpc["cloud_step"] if steps[0].fused else sum(v for n, v in bpc.items() if n != "cloud_step")) * B
+        step_bytes = steps[0].step_bytes_per_cloud() * B
+        step_flop = 8 * ((G - 1) * N + G * N + M * k * k) * B
         cpu_base, _ = time_cpu(cfg, budget_s=12.0) if not args.no_cpu_baseline else ({"value": None, "unit": "clouds/s", "cores": 0, "kind": "port", "sample": "skipped"}, 0)
         line = {"metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": desc, "B_per_gpu": B, "N": N, "G": G, "k": k, "M": M,
-                           "l2_policy": f"inputs larger than L2: ring of {ring} buffer sets x {per_set / 1e6:.1f} MB",
-                           "cuda_graph": True,
-                           "step_overlap": ((f"programmatic dependent launch inside graphs of up to {ring} steps"
-                                             if steps[0].fused else
-                                             f"independent steps round-robin on {os.environ.get('GM3D_RING_LANES', '4')} forked streams "
-                                             f"inside graphs of up to {ring} steps") if overlap else "none"),
-                           "kernels_per_step": steps[0].kernels_per_step, "collective": collective},
+                "config": cdict,
+                "reps": R, "ms_per_step_min": float(tl[0]) / K, "ms_per_step_p90": float(tl[int(0.9 * (R - 1))]) / K,
+                "timing": f"median over {R} repetitions of the {K}-step region (CUDA events per repetition, max over ranks per "
+                          "repetition; ranks aligned on the device before each repetition)",
+                "run": {"path": steps[0].path, "kernels_per_step": steps[0].kernels_per_step, "cuda_graph": True,
+                        "step_overlap": ((f"group launches chained by programmatic dependent launch, mask / loss launches on "
+                                          f"forked streams, graphs of up to {ring} steps" if steps[0].group_per_cloud else
+                                          f"independent steps round-robin on {os.environ.get('GM3D_RING_LANES', '4')} forked streams "
+                                          f"inside graphs of up to {ring} steps") if overlap else "none"),
+                        "collective": collective},
                 "clocks": clk, "e2e": e2e, "gpu_launches": steps[0].kernels_per_step * K,
                 "roofline": roofline, "roofline_detail": detail,
-                "step_hbm": {"algorithmic_bytes_per_step": step_bytes,
-                             "gbs": step_bytes / (ms / K * 1e-3) / 1e9, "frac": step_bytes / (ms / K * 1e-3) / 1e9 / hbm_peak},
-                "cpu_baseline": cpu_base, "loss_check": loss_last}
+                "step_hbm": {"algorithmic_bytes_per_step": step_bytes, "gbs": step_bytes / (us_step * 1e-6) / 1e9,
+                             "frac": step_bytes / (us_step * 1e-6) / 1e9 / hbm_peak},
+                "step_fp32": {"flop_per_step": step_flop, "tflops": step_flop / (us_step * 1e-6) / 1e12,
+                              "frac": step_flop / (us_step * 1e-6) / 1e12 / fp32_peak},
+                "single_launch": single,
+                "cpu_baseline": cpu_base, "loss_check": loss_last, "parity_check": parity, "allreduce_check": allreduce}
         print(json.dumps(line), flush=True)
+    failed = (parity is not None and parity != "ok") or (allreduce is not None and allreduce != "ok")
+    wd.cancel()
     if world > 1:
         # Captured NCCL work keeps the communicator busy at teardown (destroy_process_group / interpreter exit
         # can hang on graphs that hold collectives): synchronise, flush and leave without running destructors.
-        dist.barrier()
+        fl = torch.tensor([1.0 if failed else 0.0], device=dev)
+        dist.all_reduce(fl, op=dist.ReduceOp.MAX)
+        failed = fl.item() != 0.0
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        os._exit(1 if failed else 0)
+    if failed:
+        raise SystemExit(1)
+
+
+class _Slot:
+    """View of a PeerInbox that maps a one-step ring's slot 0 to slot `i` of the real inbox (--no-overlap)."""
+
+    def __init__(self, inbox, i):
+        self.inbox, self.i = inbox, i
+
+    def step_reduce(self, slot, head_ptr):
+        return self.inbox.step_reduce(self.i + slot, head_ptr)
 
 
 def _knn_group_only(L, s, st):
@@ -475,6 +676,11 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="one graph per step, no programmatic dependent launch")
+    ap.add_argument("--reps", type=int, default=0, help="repetitions of the K-step timed region (0: enough for --min-region-ms, at least 25)")
+    ap.add_argument("--min-region-ms", type=float, default=600.0, help="total timed time wanted (clock sampling needs a few hundred ms)")
+    ap.add_argument("--collective", default="auto", choices=["auto", "peer", "nccl", "none"],
+                    help="N > 1: per-step peer-memory all-reduce inside the loss launch (auto: if peer memory maps), or one NCCL all-reduce per graph")
+    ap.add_argument("--no-checks", action="store_true", help="skip the oracle / all-reduce checks after the timed region")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":

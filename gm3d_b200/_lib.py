@@ -11,12 +11,23 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_PKG, "libgm3d_sm100.so")
 
-GM3D_ABI_VERSION = 4
+GM3D_ABI_VERSION = 5
 GM3D_EINVAL, GM3D_ENOSUP, GM3D_EALIGN = -1, -2, -3
 OP_FPS, OP_KNN, OP_GROUP, OP_CHAMFER_FWD, OP_CHAMFER_BWD, OP_HARD_MASK, OP_LOSS_STATS, OP_CLOUD_STEP, OP_LEARNING_LOSS = range(1, 10)
 KNN_MAX_K = 32
 LOSS_STATS_LEN = 8
-STEP_OVERLAP_NEXT, STEP_OVERLAP_PREV = 1, 2
+STEP_OVERLAP_NEXT, STEP_OVERLAP_PREV, STEP_AFTER_PREV, STEP_SHARED_SMS = 1, 2, 4, 8
+MAX_PEERS = 8
+INBOX_BYTES = 2 * MAX_PEERS * 32
+
+
+class StepReduce(ctypes.Structure):
+    """gm3d_step_reduce_t (include/gm3d.h): where the tail of a loss launch publishes / all-reduces the step's
+    {sum, sum_sq, count}.  Passed by HOST pointer; the library copies it into the kernel parameters."""
+    _fields_ = [("head", ctypes.c_void_p), ("world", ctypes.c_int), ("rank", ctypes.c_int),
+                ("inbox", ctypes.c_void_p * MAX_PEERS), ("epoch", ctypes.c_void_p),
+                ("timeout_us", ctypes.c_uint), ("status", ctypes.c_void_p)]
+
 
 _vp, _i, _u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
 
@@ -32,17 +43,21 @@ SIGNATURES = {
     "gm3d_knn_group_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "gm3d_group_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gm3d_chamfer_fwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
-    "gm3d_chamfer_fused_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "gm3d_chamfer_fused_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "gm3d_chamfer_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _i, _i, _i, _vp, _vp, _vp]),
     "gm3d_select_patches_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "gm3d_hard_mask_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _u64, _u64, _vp, _vp, _vp]),
+    "gm3d_hard_mask_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _u64, _u64, _vp, _vp, _i, _vp]),
     "gm3d_loss_stats_f32": (_i, [_vp, _i, _vp, _vp]),
     "gm3d_learning_loss_f32": (_i, [_vp, _vp, _i, _i, _i, ctypes.c_float, _vp, _vp, _vp, _vp]),
     "gm3d_scale_translate_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "gm3d_gather_points_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "gm3d_encoder_fwd_bf16": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "gm3d_cloud_step_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _u64, _u64, _vp, _vp, _vp,
-                                 ctypes.c_float, ctypes.c_float, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+                                 ctypes.c_float, ctypes.c_float, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "gm3d_peer_alloc": (_i, [ctypes.c_size_t, ctypes.POINTER(_vp), ctypes.c_char_p]),
+    "gm3d_peer_open": (_i, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "gm3d_peer_close": (_i, [_vp]),
+    "gm3d_peer_free": (_i, [_vp]),
 }
 
 _lib = None

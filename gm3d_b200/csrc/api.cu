@@ -1,4 +1,6 @@
 // Host-only entry points of the C ABI (include/gm3d.h): version, error strings, workspace query.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace gm3d {
@@ -20,6 +22,50 @@ GM3D_API const char* gm3d_strerror(int code) {
     }
     if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
     return "unknown gm3d error";
+}
+
+// ---- inter-GPU inboxes of the per-step statistics all-reduce (set-up time; see gm3d_step_reduce_t) ----------
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+
+GM3D_API int gm3d_peer_alloc(size_t bytes, void** ptr, unsigned char handle[64]) {
+    if (!ptr || !handle || bytes == 0) return GM3D_EINVAL;
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaMemset(d, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, d);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return static_cast<int>(e);
+    }
+    memcpy(handle, &h, 64);
+    *ptr = d;
+    return GM3D_OK;
+}
+
+GM3D_API int gm3d_peer_open(const unsigned char handle[64], void** ptr) {
+    if (!ptr || !handle) return GM3D_EINVAL;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* d = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&d, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    *ptr = d;
+    return GM3D_OK;
+}
+
+GM3D_API int gm3d_peer_close(void* ptr) {
+    if (!ptr) return GM3D_EINVAL;
+    const cudaError_t e = cudaIpcCloseMemHandle(ptr);
+    return e == cudaSuccess ? GM3D_OK : static_cast<int>(e);
+}
+
+GM3D_API int gm3d_peer_free(void* ptr) {
+    if (!ptr) return GM3D_EINVAL;
+    const cudaError_t e = cudaFree(ptr);
+    return e == cudaSuccess ? GM3D_OK : static_cast<int>(e);
 }
 
 GM3D_API size_t gm3d_workspace_bytes(int op, int B, int N, int G, int k) {

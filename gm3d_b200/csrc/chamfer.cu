@@ -17,6 +17,9 @@
 // ..._Classifier_SVM.py:968-982.
 #include <float.h>
 
+#include <atomic>
+
+#include "chamfer_patch.cuh"
 #include "loss_reduce.cuh"
 
 namespace gm3d {
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(kCdThreads)
                   float* __restrict__ dist2, int32_t* __restrict__ idx1, int32_t* __restrict__ idx2,
                   float* __restrict__ per_patch, float* __restrict__ total, float* __restrict__ stats, int norm,
                   float gscale1, float gscale2, float* __restrict__ gxyz1, float* __restrict__ gxyz2,
-                  unsigned* __restrict__ ticket) {
+                  unsigned* __restrict__ ticket, int has_red, const __grid_constant__ gm3d_step_reduce_t red) {
     constexpr int GPW = 32 / S;  // patch pairs per warp
     __shared__ float4 s_a[kCdWarps * GPW][S];
     __shared__ float4 s_b[kCdWarps * GPW][S];
@@ -190,7 +193,79 @@ __global__ void __launch_bounds__(kCdThreads)
         }
     }
 
-    if (ticket && last_cta(ticket)) final_loss_reduce(per_patch, P, total, stats);
+    if (ticket && last_cta(ticket)) final_loss_reduce(per_patch, P, total, stats, has_red ? &red : nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// patch regime, 16 < n == m <= 32: one WARP per patch pair (chamfer_patch.cuh -- the distance matrix is evaluated
+// once, row minima in-lane, column minima by REDUX.MIN + ballot).  Persistent warps; the next patch pair (and the
+// index of the one after) is already in flight in registers while the current one is evaluated, gradients leave
+// through a shared-memory transpose as 16-byte stores.
+// ------------------------------------------------------------------------------------------------
+template <bool FUSED, int CW>
+__global__ void __launch_bounds__(CW * 32, 32 / CW)
+    chamfer_warp32(const float* __restrict__ xyz1, const float* __restrict__ xyz2, const int32_t* __restrict__ xyz2_index,
+                   int P, int k, float* __restrict__ dist1, float* __restrict__ dist2, int32_t* __restrict__ idx1,
+                   int32_t* __restrict__ idx2, float* __restrict__ per_patch, float* __restrict__ total,
+                   float* __restrict__ stats, int norm, float gscale1, float gscale2, float* __restrict__ gxyz1,
+                   unsigned* __restrict__ ticket, int vec_grad, int flags, int has_red,
+                   const __grid_constant__ gm3d_step_reduce_t red) {
+    __shared__ __align__(16) ChamferWarpScratch s_sc[CW];
+    pdl_enter(flags);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ChamferWarpScratch* sc = &s_sc[warp];
+    const int warps_total = gridDim.x * CW;
+    const int nf = 3 * k;
+    const int lc = lane < k ? lane : 0;
+    int p = blockIdx.x * CW + warp;
+    auto b_patch = [&](int q) -> size_t {
+        return xyz2_index ? static_cast<size_t>(__ldg(xyz2_index + q)) : static_cast<size_t>(q);
+    };
+    float ax = 0.f, ay = 0.f, az = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+    size_t nb = 0;  // target patch of the NEXT trip
+    if (p < P) {
+        const float* a = xyz1 + static_cast<size_t>(p) * nf + 3 * lc;
+        const float* b = xyz2 + b_patch(p) * nf + 3 * lc;
+        ax = __ldg(a), ay = __ldg(a + 1), az = __ldg(a + 2);
+        bx = __ldg(b), by = __ldg(b + 1), bz = __ldg(b + 2);
+        if (p + warps_total < P) nb = b_patch(p + warps_total);
+    }
+    for (; p < P; p += warps_total) {
+        const int pn = p + warps_total;
+        float nax = 0.f, nay = 0.f, naz = 0.f, nbx = 0.f, nby = 0.f, nbz = 0.f;
+        size_t nnb = 0;
+        if (pn < P) {  // warp-uniform
+            const float* a = xyz1 + static_cast<size_t>(pn) * nf + 3 * lc;
+            const float* b = xyz2 + nb * nf + 3 * lc;
+            nax = __ldg(a), nay = __ldg(a + 1), naz = __ldg(a + 2);
+            nbx = __ldg(b), nby = __ldg(b + 1), nbz = __ldg(b + 2);
+            if (pn + warps_total < P) nnb = b_patch(pn + warps_total);
+        }
+        const ChamferWarpOut o = chamfer_patch_warp<FUSED>(ax, ay, az, bx, by, bz, k, norm, gscale1, gscale2, lane, sc);
+        const size_t pe = static_cast<size_t>(p) * k + lane;
+        if (lane < k) {
+            if (dist1) dist1[pe] = o.dist1;
+            if (dist2) dist2[pe] = o.dist2;
+            if (idx1) idx1[pe] = o.idx1;
+            if (idx2) idx2[pe] = o.idx2;
+        }
+        if (lane == 0 && per_patch) per_patch[p] = o.per_patch;
+        if constexpr (FUSED) {
+            if (vec_grad) {  // k % 4 == 0 and a 16-byte aligned gradient tensor: 3k floats leave as 3k/4 float4
+                float* t = reinterpret_cast<float*>(sc->bg);
+                if (lane < k) t[3 * lane] = o.gx, t[3 * lane + 1] = o.gy, t[3 * lane + 2] = o.gz;
+                __syncwarp();
+                if (lane < (nf >> 2)) reinterpret_cast<float4*>(gxyz1 + static_cast<size_t>(p) * nf)[lane] = sc->bg[lane];
+                __syncwarp();
+            } else if (lane < k) {
+                float* go = gxyz1 + pe * 3;
+                go[0] = o.gx, go[1] = o.gy, go[2] = o.gz;
+            }
+        }
+        ax = nax, ay = nay, az = naz, bx = nbx, by = nby, bz = nbz, nb = nnb;
+    }
+    pdl_exit(flags);
+    if (ticket && last_cta(ticket)) final_loss_reduce(per_patch, P, total, stats, has_red ? &red : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -404,30 +479,77 @@ __global__ void __launch_bounds__(kCdThreads)
 // Workspace layout of the forward: [0,16) ticket (must be zero on entry, left zero), [16, 16+4P) per-patch scratch.
 constexpr size_t kCdWsHeader = 16;
 
+// One resident wave of CTAs for a kernel on the current device (per-device cache, relaxed atomics: every writer
+// stores the same value).
+template <typename K>
+static int resident_wave(K kern, int slot, int threads = kCdThreads) {
+    static std::atomic<int> cache[64][10];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::atomic<int>* c = (dev >= 0 && dev < 64) ? &cache[dev][slot] : nullptr;
+    int w = c ? c->load(std::memory_order_relaxed) : 0;
+    if (w == 0) {
+        int sms = 148, per_sm = 4;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0);
+        w = sms * (per_sm > 0 ? per_sm : 1);
+        if (c) c->store(w, std::memory_order_relaxed);
+    }
+    return w;
+}
+
 template <bool FUSED>
 static int launch_small(const float* xyz1, const float* xyz2, const int32_t* xyz2_index, int P, int n, int m,
                         float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, float* pp, float* total, float* stats,
-                        int norm, float g1, float g2, float* gxyz1, float* gxyz2, unsigned* ticket, cudaStream_t st) {
+                        int norm, float g1, float g2, float* gxyz1, float* gxyz2, unsigned* ticket,
+                        const gm3d_step_reduce_t* reduce, int flags, cudaStream_t st) {
     const int mx = n > m ? n : m;
+    const gm3d_step_reduce_t red = reduce ? *reduce : gm3d_step_reduce_t{};
+    const int has_red = reduce != nullptr;
+    if (n == m && n > 16 && !gxyz2) {
+        // one warp per patch pair.  Up to two resident waves of warps: one patch per warp (the work is latency-bound,
+        // parallelism first); beyond that persistent warps that all make the same number of trips (+-1).
+        const int vec_grad = FUSED && (n % 4 == 0) && (reinterpret_cast<uintptr_t>(gxyz1) % 16 == 0);
+        // 4-warp CTAs (8 KB of registers each) slip into whatever an SM has free beside the CTAs of other launches
+        const int cw = tuning_env_int("GM3D_CD_WARPS", 4) == 8 ? 8 : 4;  // 8: tuning build only
+        const int wave = (cw == 4 ? resident_wave(chamfer_warp32<FUSED, 4>, FUSED ? 8 : 9, 128)
+                                  : resident_wave(chamfer_warp32<FUSED, 8>, FUSED ? 6 : 7, 256)) * cw;
+        int trips = (P + wave - 1) / wave;
+        if (trips <= 2) trips = 1;
+        if (flags) {
+            // Chained launch (programmatic dependent launch): the successor starts only when EVERY CTA of this grid
+            // has started, and this grid's CTAs may sit waiting for the predecessor -- so the whole grid must be
+            // resident at once, beside the other kernels of the chain: one CTA per SM, persistent warps.
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const int per_sm = tuning_env_int("GM3D_CD_CHAIN_CTAS", 1);
+            trips = (P + sms * per_sm * cw - 1) / (sms * per_sm * cw);
+        }
+        trips = tuning_env_int("GM3D_CD_TRIPS", trips);
+        const int grid = (P + trips * cw - 1) / (trips * cw);
+        cudaError_t e;
+        if (cw == 4)
+            e = launch_pdl(chamfer_warp32<FUSED, 4>, dim3(grid), dim3(128), 0, st, flags, xyz1, xyz2, xyz2_index, P, n, dist1,
+                           dist2, idx1, idx2, pp, total, stats, norm, g1, g2, gxyz1, ticket, vec_grad, flags, has_red, red);
+        else
+            e = launch_pdl(chamfer_warp32<FUSED, 8>, dim3(grid), dim3(256), 0, st, flags, xyz1, xyz2, xyz2_index, P, n, dist1,
+                           dist2, idx1, idx2, pp, total, stats, norm, g1, g2, gxyz1, ticket, vec_grad, flags, has_red, red);
+        return e == cudaSuccess ? launch_status() : static_cast<int>(e);
+    }
+    if (flags) return GM3D_ENOSUP;  // chained launches: the warp-per-patch kernel only (16 < n == m <= 32, no gxyz2)
     const int S = mx <= 8 ? 8 : (mx <= 16 ? 16 : 32);
     const int per_cta = kCdWarps * (32 / S);
     const int need = (P + per_cta - 1) / per_cta;
     // persistent grid: at most one resident wave (SM count x CTAs per SM for this instantiation)
-    static int wave[3] = {0, 0, 0};
     const int wi = S == 8 ? 0 : (S == 16 ? 1 : 2);
-    if (wave[wi] == 0) {
-        int dev = 0, sms = 148, per_sm = 4;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (S == 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chamfer_small<8, FUSED>, kCdThreads, 0);
-        else if (S == 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chamfer_small<16, FUSED>, kCdThreads, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chamfer_small<32, FUSED>, kCdThreads, 0);
-        wave[wi] = sms * (per_sm > 0 ? per_sm : 1);
-    }
-    const int grid = need < wave[wi] ? need : wave[wi];
+    const int wave = S == 8 ? resident_wave(chamfer_small<8, FUSED>, wi + (FUSED ? 3 : 0))
+                            : (S == 16 ? resident_wave(chamfer_small<16, FUSED>, wi + (FUSED ? 3 : 0))
+                                       : resident_wave(chamfer_small<32, FUSED>, wi + (FUSED ? 3 : 0)));
+    const int grid = need < wave ? need : wave;
 #define GM3D_CD_LAUNCH(SS)                                                                                         \
     chamfer_small<SS, FUSED><<<grid, kCdThreads, 0, st>>>(xyz1, xyz2, xyz2_index, P, n, m, dist1, dist2, idx1, idx2, \
-                                                          pp, total, stats, norm, g1, g2, gxyz1, gxyz2, ticket)
+                                                          pp, total, stats, norm, g1, g2, gxyz1, gxyz2, ticket, has_red, red)
     if (S == 8) GM3D_CD_LAUNCH(8);
     else if (S == 16) GM3D_CD_LAUNCH(16);
     else GM3D_CD_LAUNCH(32);
@@ -452,7 +574,7 @@ GM3D_API int gm3d_chamfer_fwd_f32(const float* xyz1, const float* xyz2, const in
     if (reduce && !pp) pp = reinterpret_cast<float*>(static_cast<char*>(ws) + kCdWsHeader);
     if ((n > m ? n : m) <= 32) {
         return launch_small<false>(xyz1, xyz2, xyz2_index, P, n, m, dist1, dist2, idx1, idx2, pp, total, stats, norm, 0.f,
-                                   0.f, nullptr, nullptr, reduce ? static_cast<unsigned*>(ws) : nullptr, st);
+                                   0.f, nullptr, nullptr, reduce ? static_cast<unsigned*>(ws) : nullptr, nullptr, 0, st);
     }
     if (P > 65535) return GM3D_ENOSUP;
     chamfer_fwd_general<<<dim3((n + kCdThreads - 1) / kCdThreads, P), kCdThreads, 0, st>>>(xyz1, xyz2, nullptr, xyz2_index,
@@ -467,17 +589,20 @@ GM3D_API int gm3d_chamfer_fwd_f32(const float* xyz1, const float* xyz2, const in
 GM3D_API int gm3d_chamfer_fused_f32(const float* xyz1, const float* xyz2, const int32_t* xyz2_index, int P, int n,
                                     int m, float gscale1, float gscale2, float* dist1, float* dist2, int32_t* idx1,
                                     int32_t* idx2, float* per_patch, float* total, float* stats, int norm, float* gxyz1,
-                                    float* gxyz2, void* ws, void* stream) {
+                                    float* gxyz2, const gm3d_step_reduce_t* red, int flags, void* ws, void* stream) {
     using namespace gm3d;
     if (!xyz1 || !xyz2 || !gxyz1 || P <= 0 || n <= 0 || m <= 0) return GM3D_EINVAL;
     if (norm != 1 && norm != 2) return GM3D_EINVAL;
     if ((n > m ? n : m) > 32) return GM3D_ENOSUP;  // the fused kernel serves the patch regime
-    const bool reduce = total || stats;
+    if (red && (red->world > GM3D_MAX_PEERS || (red->world > 1 && (!red->epoch || red->rank < 0 || red->rank >= red->world))))
+        return GM3D_EINVAL;
+    const bool reduce = total || stats || red;
     if (reduce && !ws) return GM3D_EINVAL;
     float* pp = per_patch;
     if (reduce && !pp) pp = reinterpret_cast<float*>(static_cast<char*>(ws) + kCdWsHeader);
     return launch_small<true>(xyz1, xyz2, xyz2_index, P, n, m, dist1, dist2, idx1, idx2, pp, total, stats, norm, gscale1,
-                              gscale2, gxyz1, gxyz2, reduce ? static_cast<unsigned*>(ws) : nullptr, as_stream(stream));
+                              gscale2, gxyz1, gxyz2, reduce ? static_cast<unsigned*>(ws) : nullptr, red, flags,
+                              as_stream(stream));
 }
 
 GM3D_API int gm3d_chamfer_bwd_f32(const float* xyz1, const float* xyz2, const int32_t* xyz2_index,

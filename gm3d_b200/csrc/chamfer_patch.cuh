@@ -33,7 +33,8 @@ struct ChamferWarpOut {
     float gx, gy, gz;    // d loss / d a_lane
 };
 
-template <int NORM_DYNAMIC = 0>
+// BWD = false: forward only (o.gx/gy/gz undefined, bg / in scratch untouched).
+template <bool BWD = true>
 __device__ __forceinline__ ChamferWarpOut chamfer_patch_warp(float ax, float ay, float az, float bx, float by, float bz,
                                                              int k, int norm, float gscale1, float gscale2, int lane,
                                                              ChamferWarpScratch* __restrict__ sc) {
@@ -93,6 +94,11 @@ __device__ __forceinline__ ChamferWarpOut chamfer_patch_warp(float ax, float ay,
     const float v = (k & (k - 1)) == 0 ? __fadd_rn(__fmul_rn(s1, 1.0f / kf), __fmul_rn(s2, 1.0f / kf))
                                        : __fadd_rn(__fdiv_rn(s1, kf), __fdiv_rn(s2, kf));
     o.per_patch = norm == 1 ? 0.5f * v : v;
+    if constexpr (!BWD) {
+        o.gx = o.gy = o.gz = 0.0f;
+        __syncwarp();
+        return o;
+    }
 
     // backward of the mean: upstream gradient gscale (L2) or gscale * 0.5 / sqrt(d) (L1); g = 2 * that
     const float u1 = norm == 1 ? __fmul_rn(gscale1, __fdiv_rn(0.5f, f1)) : gscale1;

@@ -62,6 +62,8 @@ struct CloudStepParams {
     int dbg_mode;  // tuning aid (GM3D_CS_MODE): 1 = sampler only, 2 = no loss work, 3 = prologue/epilogue only
     int npad;  // SoA length per coordinate: max(1024, N rounded up to 128)
     int LP;    // G rounded up to a power of two (>= 64)
+    int has_red;
+    gm3d_step_reduce_t red;  // statistics publish / peer all-reduce in the tail (has_red)
 };
 
 struct CloudStepSmem {  // offsets into dynamic shared memory
@@ -102,8 +104,9 @@ __device__ __forceinline__ void st_volatile_s32(int* p, int v) {
     asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 
-static __device__ __noinline__ void final_loss_reduce_cold(const float* per_patch, int P, float* total, float* stats) {
-    final_loss_reduce(per_patch, P, total, stats);
+static __device__ __noinline__ void final_loss_reduce_cold(const float* per_patch, int P, float* total, float* stats,
+                                                           const gm3d_step_reduce_t* red) {
+    final_loss_reduce(per_patch, P, total, stats, red);
 }
 static __device__ __noinline__ void hard_mask_row_cold(const float* lrow, int L, int LP, int len_keep, int len_loss,
                                                 const float* rrow, uint64_t seed, uint64_t ctr, int row_id, uint8_t* mrow,
@@ -112,7 +115,7 @@ static __device__ __noinline__ void hard_mask_row_cold(const float* lrow, int L,
 }
 
 template <int FW, int PPT, int WARPS, bool LOSS>
-__global__ void __launch_bounds__(WARPS * 32, WARPS <= 12 ? 2 : 1) cloud_step_kernel(const __grid_constant__ CloudStepParams p) {
+__device__ __forceinline__ void cloud_step_body(const CloudStepParams& p) {
     constexpr int kCsFpsWarps = FW, kCsFpsThreads = FW * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(128) int2 s_red[2][kCsMaxFpsWarps];  // 2 x 64 bytes: the round's buffer is an XOR of the address
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 12 ? 2 : 1) cloud_step_ke
 
     // Programmatic dependent launch: the caller promised that the next kernel in the stream touches none of
     // this launch's buffers, so it may start filling SMs as soon as every CTA of this grid is resident.
-    if (p.flags & GM3D_STEP_OVERLAP_NEXT) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    pdl_enter(p.flags);
     const int N = p.N, G = p.G, k = p.k;
     const CloudStepSmem L = cloud_step_layout(N, G, p.npad, p.LP, WARPS, LOSS);
     float* sx = reinterpret_cast<float*>(smem_raw + L.sx);
@@ -366,29 +369,60 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 12 ? 2 : 1) cloud_step_ke
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
         tr[4 + warp] = clock64(), tr[61] = gt;  // (any warp's end stamp; they finish within a few us of each other)
     }
+    // A launch that did not wait for its stream predecessor (OVERLAP_PREV) must not RETIRE before it: whatever is
+    // enqueued after a chain of overlapped steps depends on the last kernel only, so completion has to be transitive.
+    // griddepcontrol.wait returns once the predecessor grid has completed and flushed; here, after this CTA's own
+    // work, it costs nothing on the critical path.
+    pdl_exit(p.flags);
     if (LOSS && p.ticket) {
-        if (last_cta(p.ticket)) final_loss_reduce_cold(p.per_patch, p.B * M, p.total, p.stats);
+        if (last_cta(p.ticket)) final_loss_reduce_cold(p.per_patch, p.B * M, p.total, p.stats, p.has_red ? &p.red : nullptr);
     }
+}
+
+// REGS == 0: the register budget follows from the CTA shape (two 12-warp CTAs or one 24-warp CTA per SM: 80);
+// REGS > 0: an explicit cap, so that more CTAs (or a CTA of another kernel) fit beside each other on an SM.
+template <int FW, int PPT, int WARPS, bool LOSS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS <= 12 ? 2 : 1) cloud_step_kernel(const __grid_constant__ CloudStepParams p) {
+    cloud_step_body<FW, PPT, WARPS, LOSS>(p);
+}
+template <int FW, int PPT, int WARPS, bool LOSS, int REGS>
+__global__ void __maxnreg__(REGS) cloud_step_kernel_r(const __grid_constant__ CloudStepParams p) {
+    cloud_step_body<FW, PPT, WARPS, LOSS>(p);
 }
 
 size_t cloud_step_workspace_bytes(int P) { return P > 0 ? 16 + static_cast<size_t>(P) * sizeof(float) : 0; }
 
-template <int FW, int PPT, int WARPS, bool LOSS>
-static int launch_cloud_step(const CloudStepParams& p, size_t smem, cudaStream_t st) {
-    auto kern = cloud_step_kernel<FW, PPT, WARPS, LOSS>;
+template <typename K>
+static int launch_cloud_step_k(K kern, int threads, const CloudStepParams& p, size_t smem, cudaStream_t st) {
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return static_cast<int>(e);
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(p.B), cfg.blockDim = dim3(WARPS * 32), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cfg.gridDim = dim3(p.B), cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = (p.flags & GM3D_STEP_OVERLAP_PREV) ? 1 : 0;  // this launch need not wait for its predecessor
+    cfg.numAttrs = (p.flags & (GM3D_STEP_OVERLAP_PREV | GM3D_STEP_AFTER_PREV)) ? 1 : 0;  // scheduled beside its predecessor
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
     return e == cudaSuccess ? launch_status() : static_cast<int>(e);
+}
+
+template <int FW, int PPT, int WARPS, bool LOSS>
+static int launch_cloud_step(const CloudStepParams& p, size_t smem, cudaStream_t st) {
+    if constexpr (WARPS == 12 && FW == 4) {
+        // The 12-warp CTA at 56 registers (a few bytes of spill): THREE CTAs per SM -- three sampling chains and 24
+        // workers per SM hide each other's latency (measured, C2: 18.9 -> 17.4 us per step; 64 / 72 / 80: 19.2 / 19.1 / 18.9).
+#ifdef GM3D_TUNING_ENV
+        const int regs = tuning_env_int("GM3D_CS_REGS", 56);
+        if (regs == 64) return launch_cloud_step_k(cloud_step_kernel_r<FW, PPT, WARPS, LOSS, 64>, WARPS * 32, p, smem, st);
+        if (regs == 72) return launch_cloud_step_k(cloud_step_kernel_r<FW, PPT, WARPS, LOSS, 72>, WARPS * 32, p, smem, st);
+        if (regs == 80) return launch_cloud_step_k(cloud_step_kernel<FW, PPT, WARPS, LOSS>, WARPS * 32, p, smem, st);
+#endif
+        return launch_cloud_step_k(cloud_step_kernel_r<FW, PPT, WARPS, LOSS, 56>, WARPS * 32, p, smem, st);
+    }
+    return launch_cloud_step_k(cloud_step_kernel<FW, PPT, WARPS, LOSS>, WARPS * 32, p, smem, st);
 }
 
 constexpr int kCsWarps = 24;  // sampler + worker warps (80 registers per thread)
@@ -421,8 +455,9 @@ int cloud_step_launch(CloudStepParams p, cudaStream_t st) {
     // 12-warp CTAs per SM (two independent FPS chains in flight, 2 x 8 workers) beat one 24-warp CTA: the
     // latency-bound chain of one cloud hides under the other cloud's work.  A lone step has one CTA per SM
     // either way and wants all 20 workers.  GM3D_CS_WARPS overrides (tuning aid).
+    const bool pair = (p.flags & (GM3D_STEP_OVERLAP_NEXT | GM3D_STEP_OVERLAP_PREV | GM3D_STEP_SHARED_SMS)) && p.N <= 1024;  // 4 sampler + 8 worker warps
+#ifdef GM3D_CS_DEBUG  // tuning build only: the production library reads no environment and keeps no state
     static const int env_warps = getenv("GM3D_CS_WARPS") ? atoi(getenv("GM3D_CS_WARPS")) : 0;
-    const bool pair = (p.flags & (GM3D_STEP_OVERLAP_NEXT | GM3D_STEP_OVERLAP_PREV)) && p.N <= 1024;  // 4 sampler + 8 worker warps
     const int warps = env_warps ? env_warps : (pair ? 12 : kCsWarps);
     static const int mode = getenv("GM3D_CS_MODE") ? atoi(getenv("GM3D_CS_MODE")) : 0;
     p.dbg_mode = mode;
@@ -435,6 +470,9 @@ int cloud_step_launch(CloudStepParams p, cudaStream_t st) {
         case 20: return cloud_step_dispatch<20>(p, loss, st);
         default: return cloud_step_dispatch<kCsWarps>(p, loss, st);
     }
+#else
+    return pair ? cloud_step_dispatch<12>(p, loss, st) : cloud_step_dispatch<kCsWarps>(p, loss, st);
+#endif
 }
 
 }  // namespace gm3d
@@ -444,7 +482,8 @@ GM3D_API int gm3d_cloud_step_f32(const float* xyz, int B, int N, int G, int k, i
                                  int len_loss, const float* rand_keys, uint64_t seed, uint64_t offset, uint8_t* mask,
                                  int32_t* patch_index, const float* pred, float gscale1, float gscale2, int norm,
                                  float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, float* per_patch, float* total,
-                                 float* stats, float* gxyz1, int flags, void* ws, void* stream) {
+                                 float* stats, float* gxyz1, int flags, const gm3d_step_reduce_t* reduce, void* ws,
+                                 void* stream) {
     using namespace gm3d;
     if (!xyz || !fps_idx || !centers || !nbhd || B <= 0 || N <= 0 || G <= 0 || k <= 0 || k > N || G > N) return GM3D_EINVAL;
     if (!cloud_step_supported(N, G, k)) return GM3D_ENOSUP;
@@ -456,15 +495,18 @@ GM3D_API int gm3d_cloud_step_f32(const float* xyz, int B, int N, int G, int k, i
         if (!mask || !gxyz1 || len_keep < 0 || len_keep >= G || len_loss < 0 || len_loss > G - len_keep) return GM3D_EINVAL;
         if (len_loss > 0 && !loss_pred) return GM3D_EINVAL;
         if (norm != 1 && norm != 2) return GM3D_EINVAL;
-        const bool reduce = total || stats;
-        if (reduce && !ws) return GM3D_EINVAL;
+        const bool reduce_any = total || stats || reduce;
+        if (reduce_any && !ws) return GM3D_EINVAL;
+        if (reduce && (reduce->world > GM3D_MAX_PEERS || (reduce->world > 1 && (!reduce->epoch || reduce->rank < 0 || reduce->rank >= reduce->world))))
+            return GM3D_EINVAL;
         p.loss_pred = loss_pred, p.len_keep = len_keep, p.len_loss = len_loss, p.rand_keys = rand_keys;
         p.seed = seed, p.offset = offset, p.mask = mask, p.patch_index = patch_index;
         p.pred = pred, p.gscale1 = gscale1, p.gscale2 = gscale2, p.norm = norm;
         p.dist1 = dist1, p.dist2 = dist2, p.idx1 = idx1, p.idx2 = idx2;
-        p.per_patch = per_patch ? per_patch : (reduce ? reinterpret_cast<float*>(static_cast<char*>(ws) + 16) : nullptr);
+        p.per_patch = per_patch ? per_patch : (reduce_any ? reinterpret_cast<float*>(static_cast<char*>(ws) + 16) : nullptr);
         p.total = total, p.stats = stats, p.gxyz1 = gxyz1;
-        p.ticket = reduce ? static_cast<unsigned*>(ws) : nullptr;
+        p.ticket = reduce_any ? static_cast<unsigned*>(ws) : nullptr;
+        if (reduce) p.red = *reduce, p.has_red = 1;
     }
     return cloud_step_launch(p, as_stream(stream));
 }

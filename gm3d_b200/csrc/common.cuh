@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "gm3d.h"
 
@@ -71,6 +72,47 @@ inline int launch_status() {
 }
 
 inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+
+// Tuning environment variables (A/B runs) exist only in builds compiled with -DGM3D_TUNING_ENV
+// (GM3D_NVCC_FLAGS=-DGM3D_TUNING_ENV python -m gm3d_b200.build --force): the production library reads no
+// environment and keeps no global state (include/gm3d.h "Conventions").
+#if defined(GM3D_CS_DEBUG) && !defined(GM3D_TUNING_ENV)
+#define GM3D_TUNING_ENV 1
+#endif
+inline int tuning_env_int(const char* name, int dflt) {
+#ifdef GM3D_TUNING_ENV
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+#else
+    (void)name;
+    return dflt;
+#endif
+}
+
+// ---- programmatic dependent launch (include/gm3d.h: GM3D_STEP_* flags) ------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prior() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// kernel entry: let the successor in, and -- for a launch that reads its predecessors' results -- wait for them
+__device__ __forceinline__ void pdl_enter(int flags) {
+    if (flags & GM3D_STEP_OVERLAP_NEXT) pdl_launch_dependents();
+    if (flags & GM3D_STEP_AFTER_PREV) pdl_wait_prior();
+}
+// kernel exit (before the last-CTA tail): a launch that started beside its predecessor must not retire before it
+__device__ __forceinline__ void pdl_exit(int flags) {
+    if (flags & GM3D_STEP_OVERLAP_PREV) pdl_wait_prior();
+}
+// Launch with the programmatic-stream-serialization attribute when `flags` ask for it.
+template <typename K, typename... Args>
+inline cudaError_t launch_pdl(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, int flags, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (flags & (GM3D_STEP_OVERLAP_PREV | GM3D_STEP_AFTER_PREV)) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
 
 // ---- mbarrier + 1-D bulk copy (TMA engine; SASS: UBLKCP) ----------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -328,7 +328,7 @@ GM3D_API int gm3d_encoder_fwd_bf16(const float* nbhd, int P, int n_points, const
     p.nbhd = nbhd, p.P = P, p.C = C, p.w1 = w1, p.b1 = b1, p.b2 = b2, p.b3 = b3, p.b4 = b4, p.out = out, p.status = status;
     p.w2 = static_cast<const __nv_bfloat16*>(w2), p.w3 = static_cast<const __nv_bfloat16*>(w3);
     p.w4 = static_cast<const __nv_bfloat16*>(w4);
-    static const int dbg = getenv("GM3D_ENC_DBG") ? atoi(getenv("GM3D_ENC_DBG")) : 0;
+    const int dbg = tuning_env_int("GM3D_ENC_DBG", 0);
     p.dbg = dbg;
     cudaError_t e = cudaFuncSetAttribute(encoder_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kEncSmem));
     if (e != cudaSuccess) return static_cast<int>(e);

@@ -238,7 +238,7 @@ GM3D_API int gm3d_fps_f32(const float* xyz, int B, int N, int G, int32_t* idx, f
     }
     if (static_cast<size_t>((N + 3) & ~3) * 12 + static_cast<size_t>(G) * 4 > 200 * 1024) return GM3D_ENOSUP;
     // few warps with 8 points per thread: one warp per SM sub-partition is the shortest chain per round
-    static const int variant = getenv("GM3D_FPS_VARIANT") ? atoi(getenv("GM3D_FPS_VARIANT")) : 0;  // tuning aid
+    const int variant = tuning_env_int("GM3D_FPS_VARIANT", 0);  // tuning build only
     if (N <= 128) return launch_fps_reg<64, 2>(xyz, B, N, G, idx, centers, st);
     if (N <= 256) return launch_fps_reg<64, 4>(xyz, B, N, G, idx, centers, st);
     if (N <= 512) return launch_fps_reg<128, 4>(xyz, B, N, G, idx, centers, st);

@@ -152,7 +152,7 @@ static int launch_knn_q(dim3 grid, cudaStream_t st, const float* ref, const floa
 static int launch_knn_group(const float* ref, const float* query, int B, int N, int G, int k, float* dist,
                             int64_t* idx, float* nbhd, float* nbhd_org, cudaStream_t st) {
     // 1024 < N <= 16384: the two-phase kernel (knn_large.cuh); GM3D_KNN_LARGE=0 keeps the streaming kernel (A/B runs)
-    static const bool large_ok = [] { const char* e = getenv("GM3D_KNN_LARGE"); return !(e && e[0] == '0'); }();
+    const bool large_ok = tuning_env_int("GM3D_KNN_LARGE", 1) != 0;  // tuning build only
     if (large_ok && N > kKlChunk && N <= kKlMaxN) {
         const int rc = launch_knn_large(ref, query, B, N, G, k, dist, idx, nbhd, nbhd_org, st);
         if (rc != GM3D_ENOSUP) return rc;
@@ -201,7 +201,7 @@ GM3D_API int gm3d_group_f32(const float* xyz, int B, int N, int G, int k, int32_
     if (N <= 2048 && B >= 96 && static_cast<long long>(G) * ((N + 1023) / 1024) <= 256)
         return gm3d_cloud_step_f32(xyz, B, N, G, k, fps_idx, centers, knn_idx, nbhd, nbhd_org, nullptr, 0, 0, nullptr, 0, 0,
                                    nullptr, nullptr, nullptr, 0.f, 0.f, 2, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                   nullptr, nullptr, nullptr, 0, nullptr, stream);
+                                   nullptr, nullptr, nullptr, 0, nullptr, nullptr, stream);
     int rc = gm3d_fps_f32(xyz, B, N, G, fps_idx, centers, ws, stream);
     if (rc != GM3D_OK) return rc;
     return launch_knn_group(xyz, centers, B, N, G, k, nullptr, knn_idx, nbhd, nbhd_org, as_stream(stream));

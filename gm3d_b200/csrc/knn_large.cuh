@@ -336,7 +336,7 @@ static int launch_knn_large(const float* ref, const float* query, int B, int N, 
     p.N = N, p.G = G, p.k = k;
     p.nchunks = (N + kKlChunk - 1) / kKlChunk;
     const size_t budget = 227 * 1024 - 1024 - 256;
-    static const int env_gw = getenv("GM3D_KL_GW") ? atoi(getenv("GM3D_KL_GW")) : 0;  // tuning aid: 4..16, even
+    const int env_gw = tuning_env_int("GM3D_KL_GW", 0);  // tuning build only: 4..16, even
     const int gw = env_gw >= 4 && env_gw <= 16 && env_gw % 2 == 0 ? env_gw : 16;
     int nq = 32;
     // smaller query blocks when the problem would leave SMs without a block, or when the keys do not fit

@@ -8,9 +8,79 @@
 
 namespace gm3d {
 
+// ---- the step's {sum, sum_sq, count} across ranks, over peer memory (include/gm3d.h: gm3d_step_reduce_t) ----------
+// Called by every thread of the tail CTA; thread 0 holds this rank's values.  Thread r < world pushes them into rank
+// r's inbox (data, then the launch counter as a release flag, both system scope), then waits for rank r's
+// contribution in the local inbox; thread 0 sums in rank order.  One NVLink store latency + one flag round: ~2-4 us,
+// on one CTA, behind the last patch of the step -- under programmatic dependent launch the next step already runs.
+struct InboxSlot {
+    float sum, sq, cnt, pad;
+    unsigned flag, pad2[3];
+};
+static_assert(sizeof(InboxSlot) == 32 && GM3D_INBOX_BYTES == 2 * GM3D_MAX_PEERS * sizeof(InboxSlot), "inbox layout");
+
+__device__ __forceinline__ void publish_step_stats(const gm3d_step_reduce_t& r, float sum, float sq, float cnt) {
+    __shared__ float s_in[GM3D_MAX_PEERS][3];
+    __shared__ unsigned s_epoch;
+    __shared__ int s_missing;
+    const int tid = threadIdx.x;
+    if (r.world <= 1 || r.epoch == nullptr) {
+        if (tid == 0 && r.head) r.head[0] = sum, r.head[1] = sq, r.head[2] = cnt, r.head[3] = 1.0f;
+        return;
+    }
+    if (tid == 0) {
+        s_epoch = *r.epoch + 1u;
+        *r.epoch = s_epoch;
+        s_in[0][0] = sum, s_in[0][1] = sq, s_in[0][2] = cnt;  // hand-over to the pushing threads
+        s_missing = 0;
+    }
+    __syncthreads();
+    const unsigned epoch = s_epoch;
+    const float v0 = s_in[0][0], v1 = s_in[0][1], v2 = s_in[0][2];
+    __syncthreads();
+    if (tid < r.world) {
+        InboxSlot* dst = static_cast<InboxSlot*>(r.inbox[tid]) + (epoch & 1u) * GM3D_MAX_PEERS + r.rank;
+        asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v0), "f"(v1), "f"(v2), "f"(0.0f) : "memory");
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&dst->flag), "r"(epoch) : "memory");
+        // wait for rank `tid`'s push of the same launch into the local inbox
+        const InboxSlot* src = static_cast<const InboxSlot*>(r.inbox[r.rank]) + (epoch & 1u) * GM3D_MAX_PEERS + tid;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        const unsigned long long limit = static_cast<unsigned long long>(r.timeout_us ? r.timeout_us : 2000000u) * 1000ull;
+        bool ok = true;
+        for (;;) {
+            unsigned f;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(&src->flag) : "memory");
+            if (f == epoch) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > limit) {
+                ok = false;
+                break;
+            }
+        }
+        float a = __int_as_float(0x7fc00000), b = a, c = a;  // NaN marks a contribution that never arrived
+        if (ok) {
+            float pad;
+            asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(pad) : "l"(src) : "memory");
+        } else {
+            atomicMax(&s_missing, tid + 1);
+        }
+        s_in[tid][0] = a, s_in[tid][1] = b, s_in[tid][2] = c;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float a = 0.f, b = 0.f, c = 0.f;
+        for (int q = 0; q < r.world; ++q) a = __fadd_rn(a, s_in[q][0]), b = __fadd_rn(b, s_in[q][1]), c = __fadd_rn(c, s_in[q][2]);
+        if (r.head) r.head[0] = a, r.head[1] = b, r.head[2] = c, r.head[3] = static_cast<float>(r.world);
+        if (s_missing && r.status) *r.status = s_missing;
+    }
+}
+
 // Deterministic final reduction over per_patch[0..P) by one CTA: total = mean, stats = [sum, sum_sq, count,
 // min, max, mean, 0, 0].  Thread t sums elements t, t+T, ... in double, then a fixed shuffle / shared tree.
-__device__ __forceinline__ void final_loss_reduce(const float* per_patch, int P, float* total, float* stats) {
+// red (or nullptr): publish / all-reduce {sum, sum_sq, count} afterwards (publish_step_stats).
+__device__ __forceinline__ void final_loss_reduce(const float* per_patch, int P, float* total, float* stats,
+                                                  const gm3d_step_reduce_t* red = nullptr) {
     __shared__ double s_sum[32], s_sq[32];
     __shared__ float s_mn[32], s_mx[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
@@ -71,6 +141,7 @@ __device__ __forceinline__ void final_loss_reduce(const float* per_patch, int P,
             stats[6] = stats[7] = 0.0f;
         }
     }
+    if (red) publish_step_stats(*red, static_cast<float>(sum), static_cast<float>(sq), static_cast<float>(P));
 }
 
 // Returns true in every thread of the CTA that arrives last at `ticket` (and resets the ticket).
@@ -84,6 +155,7 @@ __device__ __forceinline__ bool last_cta(unsigned* ticket) {
         if (s_last) *ticket = 0u;  // self-resetting: the workspace stays zeroed for the next launch
     }
     __syncthreads();
+    __threadfence();  // acquire side: the other CTAs' per-patch stores are ordered before this CTA's reads
     return s_last != 0;
 }
 

@@ -61,6 +61,27 @@ __global__ void __launch_bounds__(1024)
                   s_sel, threadIdx.x, blockDim.x, SyncCta());
 }
 
+// L <= 64 (every Point-MAE / GM3D configuration: 64 patches): one WARP per row, the row in registers
+// (hard_mask_row_warp64), 8 rows per CTA -- one wave of small CTAs instead of B single-row CTAs with
+// shared-memory sorts and CTA barriers.
+__global__ void __launch_bounds__(256)
+    hard_mask_warp64_kernel(const float* __restrict__ loss_pred, int B, int L, int len_keep, int len_loss,
+                            const float* __restrict__ rand_keys, uint64_t seed, uint64_t offset,
+                            uint8_t* __restrict__ mask, int32_t* __restrict__ patch_index, int flags) {
+    __shared__ uint8_t s_sel[8][64];
+    pdl_enter(flags);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + warp;
+    if (b < B) {
+        const int M = L - len_keep;
+        hard_mask_row_warp64(loss_pred ? loss_pred + static_cast<size_t>(b) * L : nullptr, L, len_keep, len_loss,
+                             rand_keys ? rand_keys + static_cast<size_t>(b) * L : nullptr, seed,
+                             offset + static_cast<uint64_t>(b) * L, b, mask + static_cast<size_t>(b) * L,
+                             patch_index ? patch_index + static_cast<size_t>(b) * M : nullptr, s_sel[warp], lane);
+    }
+    pdl_exit(flags);
+}
+
 // ---------------------------------------------------------------- boolean-mask patch select
 // One CTA per cloud: ordered compaction of the selected patch ids (ballot + warp prefix), then a
 // coalesced copy of each selected patch row.
@@ -130,12 +151,18 @@ GM3D_API int gm3d_gather_grad_f32(const float* gout, const int32_t* idx, int B, 
 
 GM3D_API int gm3d_hard_mask_f32(const float* loss_pred, int B, int L, int len_keep, int len_loss,
                                 const float* rand_keys, uint64_t seed, uint64_t offset, uint8_t* mask,
-                                int32_t* patch_index, void* stream) {
+                                int32_t* patch_index, int flags, void* stream) {
     using namespace gm3d;
     if (!mask || B <= 0 || L <= 0 || len_keep < 0 || len_keep > L || len_loss < 0 || len_loss > L - len_keep)
         return GM3D_EINVAL;
     if (len_loss > 0 && !loss_pred) return GM3D_EINVAL;
     if (L > 4096) return GM3D_ENOSUP;
+    if (L <= 64) {
+        const cudaError_t e = launch_pdl(hard_mask_warp64_kernel, dim3((B + 7) / 8), dim3(256), 0, as_stream(stream), flags,
+                                         loss_pred, B, L, len_keep, len_loss, rand_keys, seed, offset, mask, patch_index, flags);
+        return e == cudaSuccess ? launch_status() : static_cast<int>(e);
+    }
+    if (flags) return GM3D_ENOSUP;  // chained launches: the one-warp-per-row kernel only (L <= 64)
     int LP = 2;
     while (LP < L) LP <<= 1;
     int threads = LP / 2 < 32 ? 32 : (LP / 2 > 1024 ? 1024 : LP / 2);

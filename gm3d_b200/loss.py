@@ -46,6 +46,43 @@ class _MaskedChamfer(torch.autograd.Function):
         return gx1, None, None, None, None
 
 
+class _FusedMaskedChamfer(torch.autograd.Function):
+    """(mean loss, per-patch loss (P,)) of pred (P,n,3) against pool[patch_index] from ONE launch
+    (gm3d_chamfer_fused_f32): the upstream gradient of a mean is uniform and known, so the launch that finds the
+    arg-mins also emits d mean / d pred; backward() only scales it.  A gradient arriving through the per-patch
+    output (the reference detaches it: engine_pretrain_Classifier_SVM.py:205-215) takes the general backward."""
+
+    @staticmethod
+    def forward(ctx, pred, pool, patch_index, norm):
+        P, n, _ = pred.shape
+        m = pool.shape[1]
+        gs1, gs2 = ((1.0 / (P * n), 1.0 / (P * m)) if norm == 2 else (0.5 / (P * n), 0.5 / (P * m)))
+        r = ops.chamfer_fused(pred, pool, gs1, gs2, norm=norm, xyz2_index=patch_index, want_dist=True)
+        ctx.save_for_backward(pred, pool, patch_index, r["grad1"], r["idx1"], r["idx2"], r["dist1"], r["dist2"])
+        ctx.norm = norm
+        ctx.set_materialize_grads(False)
+        mean, pp = r["total"].reshape(()), r["per_patch"]
+        return mean, pp
+
+    @staticmethod
+    def backward(ctx, g_mean, g_pp):
+        pred, pool, patch_index, grad1, i1, i2, d1, d2 = ctx.saved_tensors
+        g = None
+        if g_mean is not None:
+            g = grad1 * g_mean
+        if g_pp is not None:
+            P, n = d1.shape
+            m = d2.shape[1]
+            u1 = (g_pp.reshape(P, 1) / n).expand(P, n)
+            u2 = (g_pp.reshape(P, 1) / m).expand(P, m)
+            if ctx.norm == 1:  # per_patch = (mean sqrt d1 + mean sqrt d2) / 2
+                u1, u2 = u1 * 0.25 / d1.sqrt(), u2 * 0.25 / d2.sqrt()
+            gx, _ = ops.chamfer_backward(pred, pool, i1, i2, u1.contiguous(), u2.contiguous(), want_grad2=False,
+                                         xyz2_index=patch_index)
+            g = gx if g is None else g + gx
+        return g, None, None, None
+
+
 def masked_patch_index(mask: torch.Tensor, num_masked: int) -> torch.Tensor:
     """(B,G) 0/1 mask (float, bool or uint8) -> (B*M,) int32 flat ids b*G+g of the masked patches, in order."""
     if mask.dtype not in (torch.bool, torch.uint8):
@@ -54,21 +91,30 @@ def masked_patch_index(mask: torch.Tensor, num_masked: int) -> torch.Tensor:
     return idx
 
 
-def forward_loss_usual(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor, per_point: str = "dist1"):
+def forward_loss_usual(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor, per_point: str = "patch"):
     """pred (N, M, n*3) or (N*M, n, 3); target = neighborhood (N, G, n, 3); mask (N, G) with M ones per row.
-    Returns {'MSE_mean', 'Chamfer_mean', 'matrix' (N, M)} like the reference (per_point: SURVEY F5)."""
+    Returns {'MSE_mean', 'Chamfer_mean', 'matrix' (N, M)} like the reference.
+
+    per_point -- GM3D's modified chamfer extension returns a per-point tensor whose exact form is not in the reference
+    tree.  ONE convention is used throughout this package (loss.py, pipeline.GroupLossStep,
+    gm3d_cloud_step_f32, ChamferDistanceL2(reduction='patch')): 'patch' -- the per-patch loss is
+    mean_n dist1 + mean_m dist2, i.e. stock ChamferDistanceL2 per patch, and the whole forward + gradient is one
+    launch.  'dist1' / 'sum' keep the two per-point candidates (matrix = mean_n of dist1, or of dist1 + dist2)."""
     N, G, n, D = target.shape
     M = pred.numel() // (N * n * D)
     index = masked_patch_index(mask, M)
     pred_ = pred.reshape(-1, n, D).to(dtype=torch.float32).contiguous()
     pool = target.reshape(N * G, n, D).to(dtype=torch.float32).contiguous()
+    if per_point == "patch":
+        mean, pp = _FusedMaskedChamfer.apply(pred_, pool, index, 2)
+        return {"MSE_mean": mean * 0.0, "Chamfer_mean": mean, "matrix": pp.reshape(N, M)}
     loss = _MaskedChamfer.apply(pred_, pool, index, 2, per_point)
     loss = loss.reshape(N, -1, n)
     return {"MSE_mean": loss.mean() * 0.0, "Chamfer_mean": loss.mean(), "matrix": loss.mean(dim=-1)}
 
 
 def forward_loss_feature(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor, point_target: torch.Tensor,
-                         point_reconstructed: torch.Tensor, per_point: str = "dist1"):
+                         point_reconstructed: torch.Tensor, per_point: str = "patch"):
     """Feature mode: normalised-feature MSE (N, M) + per-patch Chamfer (N, M)."""
     N, P_, D = target.shape
     bmask = mask if mask.dtype == torch.bool else mask != 0
@@ -82,8 +128,10 @@ def forward_loss_feature(pred: torch.Tensor, target: torch.Tensor, mask: torch.T
     index = masked_patch_index(bmask, PP)
     rec = point_reconstructed.reshape(N * PP, -1, 3).to(dtype=torch.float32).contiguous()
     pool = point_target.reshape(N * P_, n, 3).to(dtype=torch.float32).contiguous()
-    loss_chamfer = _MaskedChamfer.apply(rec, pool, index, 2, per_point)
-    loss_chamfer = loss_chamfer.reshape(N, PP, -1).mean(-1)
+    if per_point == "patch":
+        loss_chamfer = _MaskedChamfer.apply(rec, pool, index, 2, "patch").reshape(N, PP)
+    else:
+        loss_chamfer = _MaskedChamfer.apply(rec, pool, index, 2, per_point).reshape(N, PP, -1).mean(-1)
     return {"MSE_mean": loss_mse.mean(), "Chamfer_mean": loss_chamfer.mean(), "matrix": loss_mse + loss_chamfer}
 
 

@@ -220,7 +220,7 @@ def chamfer_fused(xyz1: torch.Tensor, xyz2: torch.Tensor, gscale1: float, gscale
                                                     float(gscale2), _p(out["dist1"]), _p(out["dist2"]), _p(out["idx1"]),
                                                     _p(out["idx2"]), _p(out["per_patch"]), _p(out["total"]),
                                                     _p(out["stats"]), int(norm), _p(out["grad1"]), _p(out["grad2"]),
-                                                    _p(ws), _stream(xyz1))
+                                                    None, 0, _p(ws), _stream(xyz1))
             _lib.check("gm3d_chamfer_fused_f32", rc)
     return out
 
@@ -306,7 +306,7 @@ def hard_mask(loss_pred: Optional[torch.Tensor], B: int, L: int, len_keep: int, 
         if B > 0 and L > 0:
             rc = _lib.load().gm3d_hard_mask_f32(_p(loss_pred), B, L, int(len_keep), int(len_loss), _p(rand_keys),
                                                 int(seed) & (2**64 - 1), int(offset) & (2**64 - 1), _p(mask), _p(index),
-                                                torch.cuda.current_stream(device).cuda_stream)
+                                                0, torch.cuda.current_stream(device).cuda_stream)
             _lib.check("gm3d_hard_mask_f32", rc)
     return (mask, index) if want_index else mask
 

@@ -1,21 +1,30 @@
 """One step of the grouping + reconstruction-loss path on preallocated buffers, captured as a CUDA graph.
 
     xyz (B,N,3) --group--> neighborhood (B,G,k,3), center (B,G,3)
-    loss_pred (B,G) --hard mask--> mask (B,G), M ones per row --select--> patch_index (B*M)
-    pred (B*M,k,3) vs neighborhood[patch_index] --Chamfer fwd--> dist/idx, per-patch loss (B*M), scalar loss
-    --Chamfer bwd (mean reduction)--> grad_pred (B*M,k,3);   per-patch loss --stats--> (8,) vector
-    [world_size > 1: one all-reduce of the stats vector]
+    loss_pred (B,G) --hard mask--> mask (B,G), M ones per row, patch_index (B*M)
+    pred (B*M,k,3) vs neighborhood[patch_index] --Chamfer fwd + bwd of the mean--> dist/idx, per-patch loss (B*M),
+    scalar loss, grad_pred (B*M,k,3), statistics (8,) [+ the cross-rank sum of their head]
 
 This is the per-step sequence of the reference's pre-training loop restricted to the hot path
-(/root/reference/Point-MAE_SA3D/engine_pretrain_Classifier_SVM.py:108-118,157-184,297-305).  The step issues
-4 kernels through the C ABI; replayed as one graph it has no host work between them.  `HostStagedStep`
-adds the host<->device copies from/to pinned memory (the end-to-end arm of bench.py).
+(/root/reference/Point-MAE_SA3D/engine_pretrain_Classifier_SVM.py:108-118,157-184,297-305).  In that loop
+`loss_pred` comes out of the teacher network, which consumes the grouping, and `pred` out of the student, which
+consumes the grouping AND the mask.  The step therefore runs as the three operator launches a training loop can
+interleave with its networks ("dataflow" path, the default and what bench.py times):
+
+    gm3d_group_f32 / gm3d_cloud_step_f32(pred = NULL)  ->  gm3d_hard_mask_f32  ->  gm3d_chamfer_fused_f32
+
+The "single" path issues the same work as ONE launch (gm3d_cloud_step_f32 with `pred`); it serves callers whose
+prediction does not depend on this step's grouping / mask and is reported by bench.py as `single_launch`.
+`StepRing` replays a ring of independent steps as one graph: the group launches chain by programmatic dependent
+launch on one stream, masks and Chamfer launches run on two forked streams behind their own step's group launch,
+so the loss of step i overlaps the sampling of step i+1.  `HostStagedStep` adds the host<->device copies from/to
+pinned memory (the end-to-end arm of bench.py).
 """
 from __future__ import annotations
 
+import ctypes
 import os
-
-from typing import Optional
+from typing import List, Optional
 
 import torch
 
@@ -23,27 +32,32 @@ from . import _lib
 from .masking import mask_lengths
 
 FUSED_LANES_MAX_B = int(os.environ.get("GM3D_FUSED_LANES_MAX_B", "148"))  # tuning aid
-KERNELS_PER_STEP = 4  # unfused: fps, knn_group, hard_mask (+patch index), chamfer fused (fwd + bwd + loss reduction)
-FUSED_MAX_N, FUSED_MAX_G = 2048, 1024  # gm3d_cloud_step_f32 serves these; larger clouds use the 4-kernel sequence
+FUSED_MAX_N, FUSED_MAX_G = 2048, 1024  # gm3d_cloud_step_f32 serves these; larger clouds use fps + knn_group
 
 
 class GroupLossStep:
     def __init__(self, B: int, N: int, G: int, k: int, mask_ratio: float = 0.6, epoch: int = 199,
                  total_epoch: int = 400, ratio_cap: float = 0.8, norm: int = 2, device=None, seed: int = 0,
-                 rand_offset: int = 0, fused: Optional[bool] = None):
+                 rand_offset: int = 0, fused: Optional[bool] = None, path: Optional[str] = None):
+        """path: 'dataflow' (default: group -> mask -> Chamfer launches) or 'single' (one gm3d_cloud_step_f32 launch;
+        `fused=True` is the same request, `fused=False` forces the dataflow path with separate fps / kNN kernels)."""
         self.lib = _lib.load()
         can_fuse = N <= FUSED_MAX_N and G <= FUSED_MAX_G and k <= _lib.KNN_MAX_K
-        if fused and not can_fuse:
+        if path is None:
+            path = "single" if fused else "dataflow"
+        if path not in ("dataflow", "single"):
+            raise ValueError(f"path must be 'dataflow' or 'single', got {path!r}")
+        if path == "single" and not can_fuse:
             raise NotImplementedError(f"gm3d_cloud_step_f32 serves N <= {FUSED_MAX_N}, G <= {FUSED_MAX_G}")
-        # default: one CTA per cloud pays off while the FPS chain (G dependent rounds, ~0.3 us each beside the workers)
-        # is not what the CTA waits for.  Measured on B200 against the kernel sequence spread over forked streams:
-        # C1, C2, C4, M2AE level 2 (G <= 128) fused; M2AE level 1 (G = 256: 78 us fused, 62 us as a sequence) and
-        # level 0 (G = 512) as a sequence.
-        worth = G <= 128
-        if fused is None and os.environ.get("GM3D_STEP_FUSED") in ("0", "1"):  # tuning aid (A/B runs of the two paths)
-            fused = os.environ["GM3D_STEP_FUSED"] == "1" and can_fuse
-        self.fused = (can_fuse and worth) if fused is None else fused
-        self.kernels_per_step = 1 if self.fused else KERNELS_PER_STEP
+        self.path = path
+        self.fused = path == "single"
+        # Grouping by the per-cloud kernel (sampling and patch selection overlapped inside one CTA) pays off while the
+        # FPS chain (G dependent rounds) is not what the CTA waits for; measured on B200: G <= 128 (C1, C2, C4, M2AE
+        # level 2) per-cloud kernel, M2AE levels 0 / 1 and N > 2048 as fps + knn_group.
+        self.group_per_cloud = can_fuse and G <= 128 and fused is not False
+        # the mask and Chamfer launches can join a programmatic-dependent-launch chain (StepRing) for these shapes
+        self.chainable = G <= 64 and 16 < k <= 32
+        self.kernels_per_step = 1 if self.fused else (3 if self.group_per_cloud else 4)
         self.dev = torch.device(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
         if self.dev.type != "cuda":
             raise RuntimeError("GroupLossStep runs on CUDA only (gm3d_b200 has no CPU fallback)")
@@ -99,62 +113,96 @@ class GroupLossStep:
         return {
             "fps": 12 * N + 16 * G,
             "knn_group": 12 * N + 12 * G + 12 * G * k,           # int64 idx not requested by Group
+            # Group.forward in one launch: the cloud once in, fps_idx + centres + neighbourhood out
+            "group": 12 * N + 4 * G + 12 * G + 12 * G * k,
             # fused fwd+bwd: read pred + target patches once, write dist1/2 + idx1/2, per-patch loss, grad_pred
             "chamfer_fused": 24 * M * k + 16 * M * k + 4 * M + 12 * M * k,
             "hard_mask": 5 * G + 4 * M,
-            # the fused step reads xyz, loss_pred, pred once and writes every output once; the neighbourhood,
+            # the single launch reads xyz, loss_pred, pred once and writes every output once; the neighbourhood,
             # centres and mask never come back from HBM
             "cloud_step": 12 * N + 4 * G + 12 * M * k + (4 * G + 12 * G + 12 * G * k) + (G + 4 * M)
                           + (16 * M * k + 4 * M + 12 * M * k),
         }
 
-    def enqueue(self, flags: int = 0) -> None:
-        """Enqueue the kernels of one step on torch's current stream (+ one forked side stream).  `flags`:
-        _lib.STEP_OVERLAP_* for the fused kernel (only between steps that share no buffer)."""
+    def step_bytes_per_cloud(self) -> int:
+        b = self.bytes_per_cloud()
+        if self.fused:
+            return b["cloud_step"]
+        return (b["group"] if self.group_per_cloud else b["fps"] + b["knn_group"]) + b["hard_mask"] + b["chamfer_fused"]
+
+    # ---- the three operator launches of the dataflow path (each on torch's CURRENT stream)
+    def enqueue_group(self, flags: int = 0) -> None:
+        L, p = self.lib, (lambda t: None if t is None else t.data_ptr())
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        B, N, G, k = self.B, self.N, self.G, self.k
+        if self.group_per_cloud:  # Group.forward by the per-cloud kernel; `flags` chain independent steps
+            _lib.check("gm3d_cloud_step_f32", L.gm3d_cloud_step_f32(
+                p(self.xyz), B, N, G, k, p(self.fps_idx), p(self.center), None, p(self.neighborhood), None,
+                None, 0, 0, None, 0, 0, None, None, None, 0.0, 0.0, 2, None, None, None, None, None, None, None, None,
+                flags, None, None, st))
+        else:
+            _lib.check("gm3d_group_f32", L.gm3d_group_f32(p(self.xyz), B, N, G, k, p(self.fps_idx), p(self.center), None,
+                                                          p(self.neighborhood), None, p(self.ws), st))
+
+    def enqueue_mask(self, flags: int = 0) -> None:
+        p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        _lib.check("gm3d_hard_mask_f32", self.lib.gm3d_hard_mask_f32(
+            p(self.loss_pred), self.B, self.G, self.len_keep, self.len_loss, None, self.seed, self.rand_offset,
+            p(self.mask), p(self.patch_index), flags, st))
+
+    def _gscale(self) -> float:
+        return (1.0 if self.norm == 2 else 0.5) / (self.P * self.k)  # d mean / d dist (L1: the outer /2 folded in)
+
+    def enqueue_loss(self, reduce: Optional[_lib.StepReduce] = None, flags: int = 0) -> None:
+        p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        g, k = self._gscale(), self.k
+        _lib.check("gm3d_chamfer_fused_f32", self.lib.gm3d_chamfer_fused_f32(
+            p(self.pred), p(self.neighborhood), p(self.patch_index), self.P, k, k, g, g, p(self.dist1), p(self.dist2),
+            p(self.idx1), p(self.idx2), p(self.per_patch), p(self.total), p(self.stats), self.norm, p(self.grad_pred),
+            None, ctypes.byref(reduce) if reduce is not None else None, flags, p(self.cd_ws), st))
+
+    def enqueue(self, flags: int = 0, reduce: Optional[_lib.StepReduce] = None) -> None:
+        """Enqueue the kernels of one step on torch's current stream (+ one forked side stream for the mask).
+        `flags`: _lib.STEP_OVERLAP_* for the single-launch kernel (only between steps that share no buffer)."""
         L, p = self.lib, (lambda t: None if t is None else t.data_ptr())
         main = torch.cuda.current_stream(self.dev)
-        st = main.cuda_stream
-        B, N, G, k, P = self.B, self.N, self.G, self.k, self.P
-        chk = _lib.check
-        g = (1.0 if self.norm == 2 else 0.5) / (P * k)  # d mean / d dist (L1: the outer /2 folded in)
         if self.fused:  # the whole step in one launch, one CTA per cloud
-            chk("gm3d_cloud_step_f32", L.gm3d_cloud_step_f32(
+            B, N, G, k, g = self.B, self.N, self.G, self.k, self._gscale()
+            _lib.check("gm3d_cloud_step_f32", L.gm3d_cloud_step_f32(
                 p(self.xyz), B, N, G, k, p(self.fps_idx), p(self.center), None, p(self.neighborhood), None,
                 p(self.loss_pred), self.len_keep, self.len_loss, None, self.seed, self.rand_offset, p(self.mask),
                 p(self.patch_index), p(self.pred), g, g, self.norm, p(self.dist1), p(self.dist2), p(self.idx1),
-                p(self.idx2), p(self.per_patch), p(self.total), p(self.stats), p(self.grad_pred), flags, p(self.cd_ws), st))
+                p(self.idx2), p(self.per_patch), p(self.total), p(self.stats), p(self.grad_pred), flags,
+                ctypes.byref(reduce) if reduce is not None else None, p(self.cd_ws), main.cuda_stream))
             return
-        # the mask depends only on loss_pred: fork it onto a side stream so that (also inside a captured
-        # graph) it runs concurrently with FPS, which occupies one SM per cloud and leaves the rest idle
+        # the mask depends only on loss_pred: fork it onto a side stream so that (also inside a captured graph) it
+        # runs beside the grouping
         fork, join = torch.cuda.Event(), torch.cuda.Event()
         fork.record(main)
         self.side.wait_event(fork)
-        chk("gm3d_hard_mask_f32", L.gm3d_hard_mask_f32(p(self.loss_pred), B, G, self.len_keep, self.len_loss, None,
-                                                       self.seed, self.rand_offset, p(self.mask), p(self.patch_index),
-                                                       self.side.cuda_stream))
+        with torch.cuda.stream(self.side):
+            self.enqueue_mask()
         join.record(self.side)
-        chk("gm3d_group_f32", L.gm3d_group_f32(p(self.xyz), B, N, G, k, p(self.fps_idx), p(self.center), None,
-                                               p(self.neighborhood), None, p(self.ws), st))
+        self.enqueue_group(0)
         main.wait_event(join)
-        chk("gm3d_chamfer_fused_f32", L.gm3d_chamfer_fused_f32(
-            p(self.pred), p(self.neighborhood), p(self.patch_index), P, k, k, g, g, p(self.dist1), p(self.dist2),
-            p(self.idx1), p(self.idx2), p(self.per_patch), p(self.total), p(self.stats), self.norm, p(self.grad_pred),
-            None, p(self.cd_ws), st))
+        self.enqueue_loss(reduce)
 
-    def capture(self, extra=None) -> "GroupLossStep":
-        """Capture one step (plus `extra()`, e.g. the stats all-reduce) into a CUDA graph."""
+    def capture(self, extra=None, reduce: Optional[_lib.StepReduce] = None) -> "GroupLossStep":
+        """Capture one step (plus `extra()`, e.g. a stats all-reduce) into a CUDA graph."""
         with torch.cuda.device(self.dev):
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):  # warm-up outside capture (cudaFuncSetAttribute, lazy module load)
-                self.enqueue()
+                self.enqueue(0, reduce)
                 if extra is not None:
                     extra()
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.enqueue()
+                self.enqueue(0, reduce)
                 if extra is not None:
                     extra()
             self.graph = g
@@ -168,70 +216,144 @@ class GroupLossStep:
 
 
 class StepRing:
-    """A ring of GroupLossStep buffer sets replayed as ONE CUDA graph.  The steps share no buffer, so the fused
-    kernels are chained with programmatic dependent launch: step i+1 starts filling SMs while step i drains
-    (launch latency, the cold-cloud prologue and the last-CTA loss reduction of one step hide under the next).
+    """A ring of GroupLossStep buffer sets replayed as ONE CUDA graph.  The steps share no buffer, so consecutive
+    steps overlap: the per-cloud launches chain with programmatic dependent launch (step i+1 fills SMs while step i
+    drains), and on the dataflow path the mask / Chamfer launches of step i run on forked streams behind their own
+    group launch, beside the group launch of step i+1.
 
-    `reduce_stats`: when the process group has more than one rank, the [sum, sum_sq, count] heads of all the
-    ring's statistics vectors are packed into `self.head` (n, 3) and SUM-all-reduced ONCE per replay -- the
-    reference all-reduces its loss scalars only to log them (util/misc.py:345-353), so batching the ring's
-    scalars into one collective changes no result and keeps NCCL out of the kernel-to-kernel chain."""
+    reduce -- what happens to the [sum, sum_sq, count] head of every step's loss statistics (row i of `self.head`,
+    (n, 4) f32, written by the tail of the step's loss launch; column 3 = number of ranks summed):
+      'none'  this rank's values;
+      'peer'  summed over the ranks INSIDE the loss launch, per step, over peer memory (`inbox`: dist.PeerInbox) --
+              the reference's per-step all_reduce_mean (util/misc.py:345-353) without an NCCL launch or a host sync;
+      'nccl'  this rank's values, then ONE NCCL SUM all-reduce of the whole (n, 4) tensor at the end of the graph
+              (batched: the reference reduces these scalars only to log them).
+    Every rank must replay the ring the same number of times."""
 
-    def __init__(self, steps, reduce_stats: bool = False):
-        self.steps = list(steps)
+    def __init__(self, steps, reduce: str = "none", inbox=None, reduce_stats: Optional[bool] = None,
+                 schedule: str = "lanes"):
+        """schedule (dataflow path with the per-cloud group kernel): 'lanes' = steps round-robin on forked streams
+        (default, fastest); 'chain' = one stream of launches chained by programmatic dependent launch."""
+        self.steps: List[GroupLossStep] = list(steps)
+        if schedule not in ("lanes", "chain"):
+            raise ValueError(f"schedule must be 'lanes' or 'chain', got {schedule!r}")
+        self.schedule = schedule
+        if reduce_stats is not None:  # round-1 spelling
+            reduce = "nccl" if reduce_stats else "none"
+        if reduce not in ("none", "peer", "nccl"):
+            raise ValueError(f"reduce must be 'none', 'peer' or 'nccl', got {reduce!r}")
+        if reduce == "peer" and inbox is None:
+            raise ValueError("reduce='peer' needs a dist.PeerInbox with one slot per step")
+        self.reduce = reduce
+        self.inbox = inbox
         self.graph: Optional[torch.cuda.CUDAGraph] = None
-        self.reduce_stats = reduce_stats
-        self.head = torch.zeros((len(self.steps), 3), dtype=torch.float32, device=self.steps[0].dev) if reduce_stats else None
+        dev = self.steps[0].dev
+        self.head = torch.zeros((len(self.steps), 4), dtype=torch.float32, device=dev)
+        self._red = []
+        for i in range(len(self.steps)):
+            if reduce == "peer":
+                r = inbox.step_reduce(i, self.head[i].data_ptr())
+            else:
+                r = _lib.StepReduce()
+                r.head, r.world, r.rank = self.head[i].data_ptr(), 1, 0
+            self._red.append(r)
         self._lanes = None
+        self._side = None
+
+    def _streams(self, n):
+        dev = self.steps[0].dev
+        if self._lanes is None or len(self._lanes) != n:
+            self._lanes = [torch.cuda.Stream(dev) for _ in range(n)]
+        return self._lanes
+
+    @staticmethod
+    def _chain_flags(i, n):
+        return (_lib.STEP_OVERLAP_NEXT if i + 1 < n else 0) | (_lib.STEP_OVERLAP_PREV if i > 0 else 0)
 
     def enqueue(self) -> None:
         n = len(self.steps)
         s0 = self.steps[0]
+        main = torch.cuda.current_stream(s0.dev)
         nl = max(1, min(n, int(os.environ.get("GM3D_RING_LANES", "4"))))  # tuning aid; 1 = one stream
         if s0.fused and nl > 1 and 2 * s0.B <= FUSED_LANES_MAX_B and n >= 2 * nl:
-            # Small batches (one CTA per cloud fills a fraction of the 2 x 148 CTA slots): several chains of
-            # programmatic-dependent launches side by side, one per forked stream.
-            main = torch.cuda.current_stream(s0.dev)
-            if self._lanes is None or len(self._lanes) != nl:
-                self._lanes = [torch.cuda.Stream(s0.dev) for _ in range(nl)]
+            # Single-launch steps of small batches (one CTA per cloud fills a fraction of the 2 x 148 CTA slots):
+            # several chains of programmatic-dependent launches side by side, one per forked stream.
+            lanes = self._streams(nl)
             fork = torch.cuda.Event()
             fork.record(main)
-            for li, lane in enumerate(self._lanes):
+            for li, lane in enumerate(lanes):
                 lane.wait_event(fork)
-                mine = self.steps[li::nl]
+                mine = list(range(li, n, nl))
                 with torch.cuda.stream(lane):
-                    for i, s in enumerate(mine):
-                        s.enqueue((_lib.STEP_OVERLAP_NEXT if i + 1 < len(mine) else 0) | (_lib.STEP_OVERLAP_PREV if i > 0 else 0))
+                    for j, i in enumerate(mine):
+                        self.steps[i].enqueue(self._chain_flags(j, len(mine)), self._red[i])
                 join = torch.cuda.Event()
                 join.record(lane)
                 main.wait_event(join)
-        elif not s0.fused and nl > 1:
-            # Kernel-sequence steps: the steps go round-robin to forked streams, so the FPS chain of one step -- G
-            # dependent rounds, one CTA per cloud, issue slots half empty -- runs beside the kNN / Chamfer kernels of
-            # another wherever SM resources allow (FPS CTAs of different steps pair up at N <= 2048; at N = 8192 the
-            # 20 SMs a 128-cloud FPS leaves free, and the tails of every kernel, get used).  The steps share no buffer.
-            main = torch.cuda.current_stream(s0.dev)
-            if self._lanes is None or len(self._lanes) != nl:
-                self._lanes = [torch.cuda.Stream(s0.dev) for _ in range(nl)]
+        elif s0.fused:
+            for i, s in enumerate(self.steps):
+                s.enqueue(self._chain_flags(i, n) if n > 1 else 0, self._red[i])
+        elif s0.group_per_cloud and self.schedule == "lanes":
+            # Dataflow path: every step is the plain stream-ordered sequence mask -> group -> Chamfer; the steps go
+            # round-robin to forked streams, so the latency-bound Chamfer launch of one step and the sampling chains
+            # of the other steps' group launches share the SMs (measured on B200, C2, us per step: 2 / 3 / 4 / 6 / 8
+            # streams -- see DESIGN.md 4.3; programmatic-dependent-launch chains of the three kernels: 26-31).
+            nl = max(1, min(n, int(os.environ.get("GM3D_RING_LANES", "12" if 2 * s0.B > FUSED_LANES_MAX_B else "24"))))
+            lanes = self._streams(nl)
             fork = torch.cuda.Event()
             fork.record(main)
-            for li, lane in enumerate(self._lanes):
+            for li, lane in enumerate(lanes):
                 lane.wait_event(fork)
                 with torch.cuda.stream(lane):
-                    for s in self.steps[li::nl]:
-                        s.enqueue(0)
+                    for i in range(li, n, nl):
+                        s = self.steps[i]
+                        s.enqueue_mask()
+                        s.enqueue_group(_lib.STEP_SHARED_SMS if n > 1 else 0)
+                        s.enqueue_loss(self._red[i])
+                join = torch.cuda.Event()
+                join.record(lane)
+                main.wait_event(join)
+        elif s0.group_per_cloud and s0.chainable:
+            # Dataflow path, per-cloud group kernel: ONE stream of launches chained by programmatic dependent launch,
+            #     G0 M0 | G1 C0 M1 | G2 C1 M2 | ... | C(n-1)        (G group, M mask, C Chamfer fwd + bwd)
+            # G and M read only the step's own inputs (OVERLAP_PREV: start beside the predecessor, wait for it before
+            # retiring); C reads its step's grouping and mask (AFTER_PREV: scheduled early, waits for the predecessor --
+            # and transitively for everything before it -- before touching memory).  The loss of step i thus runs
+            # beside the sampling chains of steps i+1 and i+2, inside the idle issue slots of their CTAs.
+            N_, P_, A_ = _lib.STEP_OVERLAP_NEXT, _lib.STEP_OVERLAP_PREV, _lib.STEP_AFTER_PREV
+            seq = [("g", 0), ("m", 0)]
+            for i in range(n - 1):
+                seq += [("g", i + 1), ("c", i), ("m", i + 1)]
+            seq.append(("c", n - 1))
+            for j, (kind, i) in enumerate(seq):
+                nxt = N_ if j + 1 < len(seq) else 0
+                s = self.steps[i]
+                if kind == "g":
+                    s.enqueue_group(nxt | (P_ if j > 0 else 0))
+                elif kind == "m":
+                    s.enqueue_mask(nxt | (P_ if j > 0 else 0))
+                else:
+                    s.enqueue_loss(self._red[i], nxt | (A_ if j > 0 else 0))
+        elif nl > 1:
+            # Kernel-sequence steps (N > 2048 or G > 128): the steps go round-robin to forked streams, so the FPS chain
+            # of one step -- G dependent rounds, one CTA per cloud, issue slots half empty -- runs beside the kNN /
+            # Chamfer kernels of another wherever SM resources allow.  The steps share no buffer.
+            lanes = self._streams(nl)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for li, lane in enumerate(lanes):
+                lane.wait_event(fork)
+                with torch.cuda.stream(lane):
+                    for i in range(li, n, nl):
+                        self.steps[i].enqueue(0, self._red[i])
                 join = torch.cuda.Event()
                 join.record(lane)
                 main.wait_event(join)
         else:
             for i, s in enumerate(self.steps):
-                f = 0
-                if s.fused and n > 1:
-                    f = (_lib.STEP_OVERLAP_NEXT if i + 1 < n else 0) | (_lib.STEP_OVERLAP_PREV if i > 0 else 0)
-                s.enqueue(f)
-        if self.reduce_stats:
+                s.enqueue(0, self._red[i])
+        if self.reduce == "nccl":
             import torch.distributed as dist
-            torch.stack([s.stats[:3] for s in self.steps], out=self.head)
             dist.all_reduce(self.head)
 
     def capture(self) -> "StepRing":
@@ -281,12 +403,12 @@ class HostStagedStep(GroupLossStep):
     def d2h_bytes(self) -> int:
         return self.h_res.numel()
 
-    def enqueue(self, flags: int = 0) -> None:
+    def enqueue(self, flags: int = 0, reduce: Optional[_lib.StepReduce] = None) -> None:
         if self.cloud_only:
             self.xyz.copy_(self.h_xyz, non_blocking=True)
         else:
             self.in_arena.copy_(self.h_in, non_blocking=True)
-        super().enqueue(flags)
+        super().enqueue(flags, reduce)
         self.h_res.copy_(self.res_arena, non_blocking=True)
 
 

@@ -39,6 +39,8 @@
  *     dense row-major.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
  *   - Functions only ENQUEUE work: no host synchronisation, no allocation, no global state.  They are
  *     re-entrant and may be called concurrently from several host threads on different streams.
+ *     (Exceptions, set-up time only: the gm3d_peer_* helpers allocate / map the inter-GPU inboxes.  Tuning
+ *     environment variables are read only by builds compiled with -DGM3D_TUNING_ENV.)
  *   - The caller owns inputs, outputs and workspace; the library never frees or retains a pointer.
  *     Workspace sizes come from gm3d_workspace_bytes(); a NULL workspace is accepted when that
  *     function returns 0 for the same arguments.
@@ -58,7 +60,7 @@
 extern "C" {
 #endif
 
-#define GM3D_ABI_VERSION 4
+#define GM3D_ABI_VERSION 5
 
 #define GM3D_OK 0
 #define GM3D_EINVAL (-1)  /* bad shape: B/N/G/k <= 0, k > N, G > N, NULL required pointer ...        */
@@ -77,15 +79,59 @@ extern "C" {
 
 /* Largest k gm3d_knn_f32 / gm3d_group_f32 accept (one warp holds the sorted k-list, one entry per lane). */
 #define GM3D_KNN_MAX_K 32
-/* gm3d_cloud_step_f32 flags (programmatic dependent launch).  Stream order normally makes a kernel wait for
- * the complete previous kernel; a step that shares NO buffer (inputs, outputs, workspace) with its stream
- * neighbour may drop that wait so that consecutive steps overlap tail-to-head:
+/* Launch flags of gm3d_cloud_step_f32, gm3d_hard_mask_f32 and gm3d_chamfer_fused_f32 (programmatic dependent
+ * launch).  Stream order normally makes a kernel start after the complete previous kernel; the launches of
+ * INDEPENDENT training steps (no shared input, output or workspace) may overlap instead:
  *   OVERLAP_NEXT  this launch lets the next kernel in the stream start while it is still running;
- *   OVERLAP_PREV  this launch does not wait for the previous kernel (which must have OVERLAP_NEXT set). */
+ *   OVERLAP_PREV  this launch reads NOTHING an earlier launch of the chain writes: it starts beside its
+ *                 predecessor (which must have OVERLAP_NEXT set) and only waits for it before it retires, so that
+ *                 completion stays transitive along the stream;
+ *   AFTER_PREV    this launch DOES read what earlier launches of the chain wrote (e.g. the Chamfer launch of a step
+ *                 reads that step's grouping): its CTAs are scheduled beside the predecessor but wait for the
+ *                 predecessor's completion -- and, transitively, for everything before it -- before they touch
+ *                 memory.  Only the launch latency overlaps.
+ * With these a ring of steps runs as ONE stream of launches  G0 M0 G1 C0 M1 G2 C1 ...  (G group, M mask, C Chamfer):
+ * the loss of step i executes beside the sampling chains of step i+2. */
 #define GM3D_STEP_OVERLAP_NEXT 1
 #define GM3D_STEP_OVERLAP_PREV 2
+#define GM3D_STEP_AFTER_PREV 4
+/* gm3d_cloud_step_f32 only: launches of other streams run beside this one (a ring of independent steps spread over
+ * several streams): use the small CTA shape (12 warps, three CTAs per SM) also without a programmatic chain. */
+#define GM3D_STEP_SHARED_SMS 8
 /* Number of floats gm3d_loss_stats_f32 writes. */
 #define GM3D_LOSS_STATS_LEN 8
+
+/* ---- per-step statistics all-reduce over peer memory (NVLink), fused into the tail of the loss kernels -----
+ * Replaces misc.all_reduce_mean's NCCL call + host sync per scalar (util/misc.py:345-353, call sites
+ * engine_pretrain_Classifier_SVM.py:297-305): the CTA that finishes a step's loss reduction pushes this rank's
+ * {sum, sum of squares, count} of the per-patch losses into every rank's inbox with system-scope stores, waits
+ * until the same step of every peer has arrived in its own inbox, and sums the contributions in rank order (every
+ * rank obtains bit-identical values).  A 12-byte message per step: latency-bound, no NCCL launch, no host work.
+ *
+ * Inbox of one rank for one step slot: GM3D_INBOX_BYTES bytes, zero before first use, laid out as
+ * [parity 2][source rank GM3D_MAX_PEERS]{ f32 sum, sum_sq, count, pad; u32 flag; u32 pad[3] } -- the parity is
+ * that of the slot's launch counter, so a fast peer's next launch never overwrites values still being read.
+ * All ranks must launch every step slot the same number of times (a missing peer sets *status after timeout_us). */
+#define GM3D_MAX_PEERS 8
+#define GM3D_INBOX_BYTES (2 * GM3D_MAX_PEERS * 32)
+typedef struct gm3d_step_reduce {
+    float* head;    /* 4 floats {sum, sum_sq, count, ranks summed} of this step (e.g. row i of a packed (steps,4)
+                       tensor), or NULL.  world <= 1: this rank's own values. */
+    int world;      /* number of ranks taking part (<= GM3D_MAX_PEERS); <= 1 disables the exchange */
+    int rank;
+    void* inbox[GM3D_MAX_PEERS]; /* inbox[r]: rank r's inbox for this step slot, mapped on THIS device (inbox[rank] is local) */
+    unsigned* epoch;             /* this rank's launch counter of the step slot (device u32, zero before first use) */
+    unsigned timeout_us;         /* bound of the wait for the peers; 0 = 2 s */
+    int32_t* status;             /* device int32 or NULL: set to 1 + (first missing rank) when the wait timed out */
+} gm3d_step_reduce_t;
+
+/* HOST helpers (set-up time; they allocate and synchronise).  gm3d_peer_alloc: cudaMalloc + zero `bytes` on the
+ * current device and export a 64-byte IPC handle; gm3d_peer_open maps another process's allocation into this
+ * process (peer access enabled lazily); gm3d_peer_close / gm3d_peer_free undo them. */
+int gm3d_peer_alloc(size_t bytes, void** ptr, unsigned char handle[64]);
+int gm3d_peer_open(const unsigned char handle[64], void** ptr);
+int gm3d_peer_close(void* ptr);
+int gm3d_peer_free(void* ptr);
 
 int gm3d_abi_version(void);
 const char* gm3d_strerror(int code); /* static storage; also decodes cudaError_t values */
@@ -146,11 +192,14 @@ int gm3d_chamfer_fwd_f32(const float* xyz1, const float* xyz2, const int32_t* xy
  *   L2 (norm 2): d loss / d dist1[p,i] = gscale1, d loss / d dist2[p,j] = gscale2
  *                (ChamferDistanceL2: gscale1 = g/(P n), gscale2 = g/(P m) for an upstream scalar g)
  *   L1 (norm 1): d loss / d dist1[p,i] = gscale1 * 0.5 / sqrt(dist1[p,i])  (gscale1 = g/(2 P n)), dist2 likewise
- * dist1, dist2, idx1, idx2, per_patch, total, stats and gxyz2 may each be NULL; gxyz1 is required. */
+ * dist1, dist2, idx1, idx2, per_patch, total, stats and gxyz2 may each be NULL; gxyz1 is required.
+ * reduce (HOST pointer, copied; or NULL): publish / all-reduce the step's {sum, sum_sq, count} from the tail of
+ * this launch (needs the workspace, like total / stats). */
 int gm3d_chamfer_fused_f32(const float* xyz1, const float* xyz2, const int32_t* xyz2_index /* or NULL */, int P,
                            int n, int m, float gscale1, float gscale2, float* dist1, float* dist2, int32_t* idx1,
                            int32_t* idx2, float* per_patch, float* total, float* stats, int norm /* 1|2 */,
-                           float* gxyz1, float* gxyz2 /* or NULL */, void* ws, void* stream);
+                           float* gxyz1, float* gxyz2 /* or NULL */, const gm3d_step_reduce_t* reduce /* or NULL */,
+                           int flags /* GM3D_STEP_* or 0 */, void* ws, void* stream);
 
 /* Chamfer backward, atomics-free and deterministic.  With g1[p,i] = gscale1 * gdist1[p,i] (or gscale1
  * alone when gdist1 is NULL -- the uniform upstream gradient of a mean), g2 likewise:
@@ -177,7 +226,7 @@ int gm3d_select_patches_f32(const float* nbhd, const uint8_t* mask, int B, int G
 int gm3d_hard_mask_f32(const float* loss_pred /* may be NULL iff len_loss == 0 */, int B, int L, int len_keep,
                        int len_loss, const float* rand_keys /* or NULL */, uint64_t seed, uint64_t offset,
                        uint8_t* mask, int32_t* patch_index /* (B*(L-len_keep)) flat ids b*L+i in order, or NULL */,
-                       void* stream);
+                       int flags /* GM3D_STEP_* or 0 */, void* stream);
 
 /* Per-rank loss statistics for the one small all-reduce of a step.  per_patch (P) ->
  * stats[GM3D_LOSS_STATS_LEN] = { sum, sum of squares, count, min, max, mean, 0, 0 } (deterministic). */
@@ -191,7 +240,12 @@ int gm3d_loss_stats_f32(const float* per_patch, int P, float* stats, void* strea
  * (bit-identical indices; same arithmetic and summation order for the loss and gradients).
  *   pred (B*M, k, 3) with M = G - len_keep; pred == NULL => grouping only (everything after nbhd_org ignored).
  *   ws: gm3d_workspace_bytes(GM3D_OP_CLOUD_STEP, B*M, 0, 0, 0) bytes, first 16 zero before the first launch
- *   (needed for total / stats; same ticket protocol as gm3d_chamfer_fwd_f32). */
+ *   (needed for total / stats / reduce; same ticket protocol as gm3d_chamfer_fwd_f32).
+ * The mask is drawn from (loss_pred, rand_keys | seed, offset) exactly as gm3d_hard_mask_f32 draws it: a caller
+ * whose network saw a mask from gm3d_hard_mask_f32 must pass the SAME seed and offset here.  In a training step
+ * the prediction depends on the grouping and the mask (engine_pretrain_Classifier_SVM.py:108-118), so the
+ * training-usable sequence is gm3d_group_f32 -> gm3d_hard_mask_f32 -> [network] -> gm3d_chamfer_fused_f32;
+ * this single launch serves callers whose `pred` does not depend on this launch's outputs. */
 int gm3d_cloud_step_f32(const float* xyz, int B, int N, int G, int k, int32_t* fps_idx, float* centers,
                         int64_t* knn_idx /* or NULL */, float* nbhd, float* nbhd_org /* or NULL */,
                         const float* loss_pred /* (B,G); may be NULL iff len_loss == 0 */, int len_keep, int len_loss,
@@ -199,7 +253,8 @@ int gm3d_cloud_step_f32(const float* xyz, int B, int N, int G, int k, int32_t* f
                         uint8_t* mask /* (B,G) */, int32_t* patch_index /* (B*M) or NULL */, const float* pred,
                         float gscale1, float gscale2, int norm /* 1|2 */, float* dist1, float* dist2, int32_t* idx1,
                         int32_t* idx2, float* per_patch, float* total, float* stats, float* gxyz1 /* (B*M,k,3) */,
-                        int flags /* GM3D_STEP_* or 0 */, void* ws, void* stream);
+                        int flags /* GM3D_STEP_* or 0 */, const gm3d_step_reduce_t* reduce /* HOST, or NULL */,
+                        void* ws, void* stream);
 
 /* ---- the operators either side of the hot path ------------------------------------------------ */
 

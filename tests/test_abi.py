@@ -35,7 +35,7 @@ def test_header_symbols_are_all_exported_and_bound():
 def test_version_errors_and_workspace_are_host_only():
     from gm3d_b200 import _lib
     lib = _lib.load()
-    assert lib.gm3d_abi_version() == _lib.GM3D_ABI_VERSION == 4
+    assert lib.gm3d_abi_version() == _lib.GM3D_ABI_VERSION == 5
     assert b"invalid" in lib.gm3d_strerror(_lib.GM3D_EINVAL)
     assert b"not supported" in lib.gm3d_strerror(_lib.GM3D_ENOSUP)
     assert lib.gm3d_strerror(0) == b"success"
@@ -59,14 +59,24 @@ def test_argument_validation_returns_einval_without_a_device():
     assert lib.gm3d_knn_group_f32(p, p, 1, 8, 2, 4, None, None, None, None) == E    # nbhd required
     assert lib.gm3d_chamfer_fwd_f32(p, p, None, 4, 8, 8, p, p, p, p, None, None, None, 3, None, None) == E  # norm
     assert lib.gm3d_chamfer_fwd_f32(p, p, None, 4, 8, 8, p, p, p, p, None, p, None, 2, None, None) == E     # total needs ws
-    assert lib.gm3d_chamfer_fused_f32(p, p, None, 4, 40, 8, 1.0, 1.0, None, None, None, None, None, None, None, 2, p, None, None, None) == U
+    assert lib.gm3d_chamfer_fused_f32(p, p, None, 4, 40, 8, 1.0, 1.0, None, None, None, None, None, None, None, 2, p, None, None, 0, None, None) == U
     assert lib.gm3d_chamfer_bwd_f32(p, p, None, None, p, None, None, 1.0, 1.0, 4, 8, 8, p, None, None) == E
-    assert lib.gm3d_hard_mask_f32(None, 2, 64, 25, 15, None, 0, 0, p, None, None) == E  # len_loss > 0 needs loss_pred
-    assert lib.gm3d_hard_mask_f32(p, 2, 64, 25, 40, None, 0, 0, p, None, None) == E     # len_loss > L - len_keep
-    assert lib.gm3d_hard_mask_f32(p, 2, 5000, 25, 4, None, 0, 0, p, None, None) == U
+    assert lib.gm3d_hard_mask_f32(None, 2, 64, 25, 15, None, 0, 0, p, None, 0, None) == E  # len_loss > 0 needs loss_pred
+    assert lib.gm3d_hard_mask_f32(p, 2, 64, 25, 40, None, 0, 0, p, None, 0, None) == E     # len_loss > L - len_keep
+    assert lib.gm3d_hard_mask_f32(p, 2, 5000, 25, 4, None, 0, 0, p, None, 0, None) == U
     assert lib.gm3d_select_patches_f32(None, p, 2, 64, 96, 65, 0, None, p, None, None) == E
     assert lib.gm3d_gather_f32(p, p, 1, 0, 8, 2, p, None) == E
     assert lib.gm3d_loss_stats_f32(None, 4, p, None) == E
+    # the per-step peer all-reduce descriptor: more ranks than inboxes, or a rank outside the world
+    red = _lib.StepReduce()
+    red.world, red.rank, red.epoch = _lib.MAX_PEERS + 1, 0, 16
+    assert lib.gm3d_chamfer_fused_f32(p, p, None, 4, 8, 8, 1.0, 1.0, None, None, None, None, None, None, None, 2, p, None,
+                                      ctypes.byref(red), 0, p, None) == E
+    red.world, red.rank = 2, 2
+    assert lib.gm3d_chamfer_fused_f32(p, p, None, 4, 8, 8, 1.0, 1.0, None, None, None, None, None, None, None, 2, p, None,
+                                      ctypes.byref(red), 0, p, None) == E
+    assert ctypes.sizeof(_lib.StepReduce) == 104 and _lib.INBOX_BYTES == 512
+    assert lib.gm3d_peer_alloc(0, None, None) == E and lib.gm3d_peer_open(None, None) == E
     with pytest.raises(ValueError):
         _lib.check("x", E)
     with pytest.raises(NotImplementedError):

@@ -541,6 +541,42 @@ def test_forward_loss_matches_reference_golden(cuda, golden):
     assert np.isclose(ChamferDistanceL1()(pred.reshape(-1, 32, 3), gt).item(), golden["cdl1_scalar"], rtol=RTOL)
 
 
+def test_forward_loss_fused_default_agrees_with_the_step(cuda):
+    """One per-patch convention everywhere: forward_loss_usual(...)['matrix'] is bit-identical to
+    GroupLossStep.per_patch.view(B, M) on the same inputs, 'Chamfer_mean' to step.total, and backward() through the
+    fused autograd Function returns the step's grad_pred; a gradient sent through 'matrix' matches float64 autograd."""
+    from gm3d_b200 import loss
+    from gm3d_b200.group import Group
+    from gm3d_b200.pipeline import GroupLossStep
+    B, N, G, k = 6, 1024, 64, 32
+    rng = np.random.default_rng(41)
+    s = GroupLossStep(B, N, G, k, 0.6, device=cuda, seed=7, rand_offset=5)
+    x = synthetic_clouds(B, N, 55)
+    s.xyz.copy_(dev(x, cuda))
+    s.loss_pred.copy_(dev(rng.standard_normal((B, G)).astype(np.float32), cuda))
+    s.pred.copy_(dev((rng.standard_normal((s.P, k, 3)) * 0.08).astype(np.float32), cuda))
+    s.run()
+    torch.cuda.synchronize()
+    nb, _ = Group(G, k)(s.xyz)
+    assert torch.equal(nb, s.neighborhood)
+    pred = s.pred.clone().reshape(B, s.M, k * 3).requires_grad_(True)
+    r = loss.forward_loss_usual(pred, nb, s.mask.view(torch.bool))
+    assert torch.equal(r["matrix"], s.per_patch.view(B, s.M))
+    assert torch.equal(r["Chamfer_mean"], s.total.reshape(()))
+    r["Chamfer_mean"].backward()
+    assert torch.equal(pred.grad.reshape(s.P, k, 3), s.grad_pred)
+    # a gradient through the per-patch matrix (the reference detaches it; autograd must still be right)
+    pred2 = s.pred.clone().requires_grad_(True)
+    r2 = loss.forward_loss_usual(pred2, nb, s.mask.view(torch.bool))
+    wgt = torch.rand(B, s.M, device=cuda)
+    (r2["matrix"] * wgt).sum().backward()
+    p64 = s.pred.double().requires_grad_(True)
+    gt64 = nb.reshape(B * G, k, 3)[s.patch_index.long()].double()
+    d = ((p64[:, :, None] - gt64[:, None]) ** 2).sum(-1)
+    ((d.min(2).values.mean(1) + d.min(1).values.mean(1)) * wgt.reshape(-1).double()).sum().backward()
+    assert (pred2.grad.double() - p64.grad).abs().max() <= RTOL * p64.grad.abs().max()
+
+
 def test_loss_stats(cuda):
     from gm3d_b200 import ops
     v = torch.rand(4992, device=cuda)
@@ -581,7 +617,7 @@ def test_cloud_step_fused_equals_kernel_sequence_and_oracle(cuda, kind, B, N, G,
     from gm3d_b200.pipeline import GroupLossStep
     x = synthetic_clouds(B, N, 77 + N + G, kind)
     rng = np.random.default_rng(5)
-    steps = [GroupLossStep(B, N, G, k, ratio, device=cuda, seed=11, rand_offset=3, norm=norm, fused=f) for f in (True, False)]
+    steps = [GroupLossStep(B, N, G, k, ratio, device=cuda, seed=11, rand_offset=3, norm=norm, fused=f) for f in (True, False, None)]
     M = steps[0].M
     lp = rng.standard_normal((B, G)).astype(np.float32)
     pred = (rng.standard_normal((B * M, k, 3)) * 0.08).astype(np.float32)
@@ -592,11 +628,13 @@ def test_cloud_step_fused_equals_kernel_sequence_and_oracle(cuda, kind, B, N, G,
             t.fill_(0)  # outputs must be fully written by the step itself
         s.run()
     torch.cuda.synchronize()
-    f, u = steps
-    assert f.kernels_per_step == 1 and u.kernels_per_step == 4
+    f, u, d = steps  # single launch; fps + knn + mask + chamfer; the default dataflow path (group -> mask -> chamfer)
+    assert f.kernels_per_step == 1 and u.kernels_per_step == 4 and d.path == "dataflow" and not d.fused
+    assert d.kernels_per_step == (3 if G <= 128 else 4)
     for name in ("fps_idx", "center", "neighborhood", "mask", "patch_index", "dist1", "dist2", "idx1", "idx2",
                  "per_patch", "total", "stats", "grad_pred"):
         assert np.array_equal(host(getattr(f, name)), host(getattr(u, name))), name
+        assert np.array_equal(host(getattr(f, name)), host(getattr(d, name))), name
     # oracle
     w = co.group(x, G, k)
     assert np.array_equal(host(f.fps_idx), w["fps_idx"])
@@ -615,6 +653,13 @@ def test_cloud_step_fused_equals_kernel_sequence_and_oracle(cuda, kind, B, N, G,
         g = np.full((B * M, k), 1.0 / (B * M * k), dtype=np.float32)
         ga, _ = co.chamfer_bwd(pred, gt, i1, i2, g, g)
         assert np.abs(host(f.grad_pred) - ga).max() <= RTOL * np.abs(ga).max()
+    else:  # L1: d mean(sqrt d)/2 / d dist = 0.5 / (P k) * 0.5 / sqrt(d); float64 oracle, patches without a zero distance
+        with np.errstate(divide="ignore"):
+            g1 = np.float32(0.5 / (B * M * k)) * (np.float32(0.5) / np.sqrt(d1))
+            g2 = np.float32(0.5 / (B * M * k)) * (np.float32(0.5) / np.sqrt(d2))
+        ok = np.isfinite(g1).all(axis=1) & np.isfinite(g2).all(axis=1)
+        ta, _ = no.chamfer_bwd(pred[ok], gt[ok], i1[ok], i2[ok], g1[ok], g2[ok])
+        assert ok.any() and np.abs(host(f.grad_pred)[ok] - ta).max() <= 1e-4 * np.abs(ta).max()
     # second run through a captured graph gives the same bits (ticket self-reset, no stale state)
     before = {n: host(getattr(f, n)).copy() for n in ("neighborhood", "grad_pred", "total", "mask")}
     f.capture()
@@ -629,14 +674,18 @@ def test_cloud_step_rejects_unsupported(cuda):
     from gm3d_b200.pipeline import GroupLossStep
     with pytest.raises(NotImplementedError):
         GroupLossStep(2, 4096, 64, 32, device=cuda, fused=True)
-    s = GroupLossStep(2, 4096, 64, 32, device=cuda)  # falls back to the kernel sequence by itself
-    assert not s.fused
-    assert GroupLossStep(128, 1024, 64, 32, device=cuda).fused          # BASELINE config[1]
-    assert not GroupLossStep(128, 2048, 512, 16, device=cuda).fused     # M2AE level 0: too much selection work per CTA
+    with pytest.raises(NotImplementedError):
+        GroupLossStep(2, 4096, 64, 32, device=cuda, path="single")
+    s = GroupLossStep(2, 4096, 64, 32, device=cuda)  # the dataflow path with separate fps / kNN kernels
+    assert not s.fused and not s.group_per_cloud and s.kernels_per_step == 4
+    c2 = GroupLossStep(128, 1024, 64, 32, device=cuda)                   # BASELINE config[1]: group -> mask -> chamfer
+    assert c2.path == "dataflow" and c2.group_per_cloud and c2.kernels_per_step == 3
+    assert GroupLossStep(128, 1024, 64, 32, device=cuda, path="single").fused
+    assert not GroupLossStep(128, 2048, 512, 16, device=cuda).group_per_cloud  # M2AE level 0: too much selection work per CTA
     lib = _lib.load()
     p = s.xyz.data_ptr()
     assert lib.gm3d_cloud_step_f32(p, 2, 4096, 64, 32, p, p, None, p, None, None, 0, 0, None, 0, 0, None, None, None,
-                                   0.0, 0.0, 2, None, None, None, None, None, None, None, None, 0, None, None) == _lib.GM3D_ENOSUP
+                                   0.0, 0.0, 2, None, None, None, None, None, None, None, None, 0, None, None, None) == _lib.GM3D_ENOSUP
 
 
 def test_step_ring_overlapped_steps_equal_serial_steps(cuda):
@@ -695,6 +744,110 @@ def test_step_ring_kernel_sequence_lanes_equal_serial_steps(cuda):
             assert np.array_equal(host(getattr(s, n)), v), n
     w0 = co.group(clouds[3], G, k)
     assert np.array_equal(host(steps[3].fps_idx), w0["fps_idx"]) and np.array_equal(host(steps[3].neighborhood), w0["neighborhood"])
+
+
+def test_step_ring_dataflow_equals_serial_steps(cuda):
+    """The dataflow ring (group launches chained by programmatic dependent launch, masks and Chamfer launches on
+    forked streams) gives, for every step, the bits of the same step run alone -- also with a deliberately LONG first
+    step in front of short ones (4x the clouds would be a different shape; here: the first step's buffers are
+    re-used by nobody, and completion must still be transitive along the chain)."""
+    from gm3d_b200.pipeline import GroupLossStep, StepRing
+    B, N, G, k = 16, 1024, 64, 32
+    rng = np.random.default_rng(29)
+    steps, want = [], []
+    for r in range(7):
+        s = GroupLossStep(B, N, G, k, 0.6, device=cuda, seed=4, rand_offset=r * B * G)
+        assert s.path == "dataflow" and s.group_per_cloud
+        s.xyz.copy_(dev(synthetic_clouds(B, N, 900 + r), cuda))
+        s.loss_pred.copy_(dev(rng.standard_normal((B, G)).astype(np.float32), cuda))
+        s.pred.copy_(dev((rng.standard_normal((s.P, k, 3)) * 0.08).astype(np.float32), cuda))
+        s.run()
+        torch.cuda.synchronize()
+        want.append({n: host(getattr(s, n)).copy() for n in ("fps_idx", "center", "neighborhood", "mask", "patch_index",
+                                                             "dist1", "idx2", "per_patch", "total", "stats", "grad_pred")})
+        for n in want[-1]:
+            getattr(s, n).fill_(0)
+        steps.append(s)
+    ring = StepRing(steps).capture()
+    for _ in range(3):
+        ring.run()
+    torch.cuda.synchronize()
+    for i, (s, w) in enumerate(zip(steps, want)):
+        for n, v in w.items():
+            assert np.array_equal(host(getattr(s, n)), v), (i, n)
+        assert np.array_equal(host(ring.head[i, :3]), host(s.stats[:3])) and ring.head[i, 3].item() == 1.0
+
+
+@pytest.mark.parametrize("path", ["dataflow", "single"])
+def test_step_ring_bench_variant_every_slot_vs_oracle(cuda, path):
+    """The exact variant bench.py times -- a ring of 24 x (B=128, N=1024, G=64, k=32) steps replayed as ONE graph
+    (12-warp per-cloud CTAs chained by programmatic dependent launch, Chamfer launches on a forked stream) -- with
+    EVERY slot's fps_idx / neighbourhood / mask / dist / idx / grad_pred against the CPU oracle."""
+    import bench
+    from gm3d_b200.pipeline import GroupLossStep, StepRing
+    B, N, G, k, ratio = bench.CONFIGS["c2"][:5]
+    ring_n = 24
+    steps, inputs = [], []
+    for r in range(ring_n):
+        s = GroupLossStep(B, N, G, k, ratio, device=cuda, seed=1234, rand_offset=r * B * G, path=path)
+        x, lp, pred = bench.synthetic_batch(B, N, G, k, s.M, 1234 + r)
+        s.xyz.copy_(dev(x, cuda)); s.loss_pred.copy_(dev(lp, cuda)); s.pred.copy_(dev(pred, cuda))
+        steps.append(s)
+        inputs.append((x, lp, pred))
+    ring = StepRing(steps).capture()
+    for s in steps:
+        for t in (s.fps_idx, s.center, s.neighborhood, s.mask, s.patch_index, s.dist1, s.dist2, s.idx1, s.idx2,
+                  s.per_patch, s.total, s.grad_pred, s.stats):
+            t.fill_(0)
+    ring.run()
+    ring.run()
+    torch.cuda.synchronize()
+    for i, s in enumerate(steps):
+        assert bench.oracle_check_step(s, *inputs[i]) == "ok", i
+        assert np.array_equal(host(ring.head[i, :3]), host(s.stats[:3]))
+
+
+def test_peer_reduce_two_ranks_on_one_gpu(cuda):
+    """The per-step statistics all-reduce over peer memory (gm3d_step_reduce_t), with both 'ranks' played by two
+    streams of ONE GPU sharing two local inboxes: each rank's head must hold rank0 + rank1 (summed in rank order, so
+    bit-identical on both), over several launches (launch-counter parity), and a missing peer must time out into
+    `status` instead of hanging."""
+    from gm3d_b200 import _lib
+    from gm3d_b200.pipeline import GroupLossStep
+    B, N, G, k = 4, 256, 64, 8
+    rng = np.random.default_rng(3)
+    inbox = torch.zeros((2, _lib.INBOX_BYTES), dtype=torch.uint8, device=cuda)
+    epoch = torch.zeros((2,), dtype=torch.int32, device=cuda)
+    status = torch.zeros((2,), dtype=torch.int32, device=cuda)
+    head = torch.zeros((2, 4), dtype=torch.float32, device=cuda)
+    ranks, reds, streams = [], [], [torch.cuda.Stream(cuda), torch.cuda.Stream(cuda)]
+    for r in range(2):
+        s = GroupLossStep(B, N, G, k, 0.6, device=cuda, seed=r, rand_offset=0)
+        s.xyz.copy_(dev(synthetic_clouds(B, N, 40 + r), cuda))
+        s.loss_pred.copy_(dev(rng.standard_normal((B, G)).astype(np.float32), cuda))
+        s.pred.copy_(dev((rng.standard_normal((s.P, k, 3)) * 0.08).astype(np.float32), cuda))
+        red = _lib.StepReduce()
+        red.head, red.world, red.rank = head[r].data_ptr(), 2, r
+        red.inbox[0], red.inbox[1] = inbox[0].data_ptr(), inbox[1].data_ptr()
+        red.epoch, red.timeout_us, red.status = epoch[r:].data_ptr(), 500_000, status[r:].data_ptr()
+        ranks.append(s)
+        reds.append(red)
+    torch.cuda.synchronize()
+    for it in range(3):
+        for r in (it % 2, 1 - it % 2):  # alternate which rank is enqueued first
+            with torch.cuda.stream(streams[r]):
+                ranks[r].enqueue(0, reds[r])
+        torch.cuda.synchronize()
+        a, b = ranks[0].stats[:3], ranks[1].stats[:3]
+        want = host(a + b)
+        assert np.array_equal(host(head[0, :3]), want) and np.array_equal(host(head[1, :3]), want), it
+        assert host(head[:, 3]).tolist() == [2.0, 2.0] and host(status).tolist() == [0, 0]
+        assert host(epoch).tolist() == [it + 1, it + 1]
+    # a peer that never launches: rank 0 alone must come back (NaN head, status = 1 + missing rank) within the timeout
+    with torch.cuda.stream(streams[0]):
+        ranks[0].enqueue(0, reds[0])
+    torch.cuda.synchronize()
+    assert status[0].item() == 2 and np.isnan(host(head[0, :3])).all()
 
 
 # ------------------------------------------------------------------------------------------ SURVEY 8(f) rows

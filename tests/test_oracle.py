@@ -80,6 +80,41 @@ def test_fps_thread_order_tie_mode():
     assert co.fps(xyz, 2, tie="pointnet2_thread_order", block=2)[0, 1] == 2
 
 
+def test_fps_tie_rules_agree_on_the_baseline_inputs():
+    """The contract resolves equal running-min distances to the lowest point index; upstream pointnet2 resolves them
+    by its block-reduction thread order.  On the BASELINE inputs (bench.synthetic_batch, the seeds
+    bench.py uses, continuous coordinates) no round ever sees a tie, so the two rules select identical indices and
+    the contract choice is immaterial there."""
+    import bench
+    for name in ("c1", "c2", "c3l0", "c3l1", "c3l2", "c4", "c5"):
+        B, N, G, k, ratio, _ = bench.CONFIGS[name]
+        Bs = min(B, 16)  # the generator draws cloud by cloud in order: the first clouds of the bench batch
+        x, _, _ = bench.synthetic_batch(B, N, G, 1, 1, 1234)
+        x = x[:Bs]
+        a = co.fps(x, G, tie="lowest_index")
+        b = co.fps(x, G, tie="pointnet2_thread_order")
+        assert int((a != b).sum()) == 0, name
+
+
+def test_fps_tie_rules_diverge_only_at_exact_ties():
+    """With exact duplicate points the two rules may pick different indices -- but always points of bit-equal
+    coordinates or bit-equal running-min distance in that round; the divergence is counted, not hidden."""
+    x = synthetic_clouds(8, 1024, 5, "sphere")  # ~1 % exact duplicates
+    G = 256
+    a = co.fps(x, G, tie="lowest_index")
+    b = co.fps(x, G, tie="pointnet2_thread_order")
+    diff = np.argwhere(a != b)
+    for bi in np.unique(diff[:, 0]):
+        j = diff[diff[:, 0] == bi][:, 1].min()          # first round where the rules part
+        pa, pb = x[bi, a[bi, j]], x[bi, b[bi, j]]
+        sel = x[bi, a[bi, :j]]                           # centres chosen so far (identical under both rules)
+        da = ((sel - pa) ** 2).sum(-1).min()
+        db = ((sel - pb) ** 2).sum(-1).min()
+        assert np.isclose(da, db, rtol=1e-6), (bi, j)    # same running-min distance (to rounding): a genuine tie
+    # lowest_index never picks a higher index than thread order could justify: indices are valid either way
+    assert a.min() >= 0 and a.max() < 1024 and b.min() >= 0 and b.max() < 1024
+
+
 def test_numpy_fps_pin(golden):
     """The in-tree CPU FPS (datasets/ModelNetDataset.py:25-46) selects the points our restatement selects."""
     pts = golden["npfps_points"]

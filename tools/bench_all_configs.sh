@@ -5,5 +5,5 @@ import json,sys
 t=sys.stdin.read().strip()
 if not t: print('FAILED'); sys.exit(0)
 d=json.loads(t.splitlines()[-1]); r=d['roofline']
-print(round(d['value']), 'clouds/s', round(d['ms_per_step']*1e3,1), 'us/step  e2e', round(d['e2e']['value']), ' kernels/step', d['config']['kernels_per_step'], ' hbm_frac', round(r['frac'],4), r['kernel'], json.dumps({k:v['us_per_launch'] for k,v in d['roofline_detail'].items()}))
+print(round(d['value']), 'clouds/s', round(d['ms_per_step']*1e3,1), 'us/step  e2e', round(d['e2e']['value']), ' kernels/step', d['run']['kernels_per_step'], ' hbm_frac', round(r['frac'],4), r['kernel'], json.dumps({k:v['us_per_launch'] for k,v in d['roofline_detail'].items()}))
 "; done

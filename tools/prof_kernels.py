@@ -32,16 +32,19 @@ torch.cuda.synchronize()
 kern = {
     "fps": lambda: L.gm3d_fps_f32(p(s.xyz), B, N, G, p(s.fps_idx), p(s.center), None, st),
     "knn_group": lambda: L.gm3d_knn_group_f32(p(s.xyz), p(s.center), B, N, G, k, None, p(s.neighborhood), None, st),
-    "hard_mask": lambda: L.gm3d_hard_mask_f32(p(s.loss_pred), B, G, s.len_keep, s.len_loss, None, 1, 0, p(s.mask), p(s.patch_index), st),
+    "hard_mask": lambda: L.gm3d_hard_mask_f32(p(s.loss_pred), B, G, s.len_keep, s.len_loss, None, 1, 0, p(s.mask), p(s.patch_index), 0, st),
     "chamfer_fused": lambda: L.gm3d_chamfer_fused_f32(p(s.pred), p(s.neighborhood), p(s.patch_index), s.P, k, k, g, g, p(s.dist1),
                                                       p(s.dist2), p(s.idx1), p(s.idx2), p(s.per_patch), p(s.total), p(s.stats), 2,
-                                                      p(s.grad_pred), None, p(s.cd_ws), st),
+                                                      p(s.grad_pred), None, None, 0, p(s.cd_ws), st),
 }
 if N <= 2048:
     kern["cloud_step"] = lambda: L.gm3d_cloud_step_f32(
         p(s.xyz), B, N, G, k, p(s.fps_idx), p(s.center), None, p(s.neighborhood), None, p(s.loss_pred), s.len_keep,
         s.len_loss, None, 1, 0, p(s.mask), p(s.patch_index), p(s.pred), g, g, 2, p(s.dist1), p(s.dist2), p(s.idx1),
-        p(s.idx2), p(s.per_patch), p(s.total), p(s.stats), p(s.grad_pred), 0, p(s.cd_ws), st)
+        p(s.idx2), p(s.per_patch), p(s.total), p(s.stats), p(s.grad_pred), 0, None, p(s.cd_ws), st)
+    kern["group"] = lambda: L.gm3d_cloud_step_f32(
+        p(s.xyz), B, N, G, k, p(s.fps_idx), p(s.center), None, p(s.neighborhood), None, None, 0, 0, None, 0, 0,
+        None, None, None, 0.0, 0.0, 2, None, None, None, None, None, None, None, None, 0, None, None, st)
 for name, fn in kern.items():
     if a.only and a.only != name:
         continue
