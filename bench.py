@@ -268,19 +268,23 @@ def run_native(args, cfg):
     mode = "none"
     if world > 1:
         mode = args.collective
-        if mode in ("auto", "peer"):
+        if mode in ("auto", "peer", "peer_sync", "peer_step"):
             from gm3d_b200.dist import PeerInbox
             try:
                 inbox = PeerInbox(ring)
-                mode = "peer"
+                mode = "peer" if mode == "auto" else mode
             except (RuntimeError, NotImplementedError) as e:  # raised on every rank together
                 _stage(f"peer memory unavailable ({e}); falling back to NCCL")
-                if args.collective == "peer":
+                if args.collective != "auto":
                     raise
                 mode = "nccl"
     collective = {"none": "none",
-                  "peer": "per step, inside the loss launch: {sum, sum_sq, count} pushed to every rank's inbox over "
-                          "NVLink peer memory and summed in rank order (gm3d_step_reduce_t)",
+                  "peer": "per step over NVLink peer memory: every loss launch pushes {sum, sum_sq, count} to every rank's "
+                          "inbox; one collect launch per graph of steps, beside the next graph's launches, sums them in "
+                          "rank order (gm3d_step_reduce_t: defer + lagging collect)",
+                  "peer_sync": "as peer, but the collect launch closes the same graph (one wait for the slowest rank per graph)",
+                  "peer_step": "per step, inside the loss launch: {sum, sum_sq, count} pushed to every rank's inbox over "
+                               "NVLink peer memory, waited for and summed in rank order by the same launch",
                   "nccl": "one NCCL all-reduce of the packed (steps, 4) statistics per graph of steps"}[mode]
 
     # ring of buffer sets larger than L2 so every step reads cold inputs and writes cold outputs
@@ -371,7 +375,12 @@ def run_native(args, cfg):
     barrier()
     clk = clocks.stop() if rank == 0 else None
     times = torch.tensor([ev0[r].elapsed_time(ev1[r]) for r in range(R)], device=dev)
+    rank_medians = [float(times.median().item()) / K]
     if world > 1:
+        own = times.median().reshape(1) / K
+        allm = [torch.empty_like(own) for _ in range(world)]
+        dist.all_gather(allm, own)
+        rank_medians = [float(t.item()) for t in allm]  # each rank's own median, before the max over ranks
         dist.all_reduce(times, op=dist.ReduceOp.MAX)  # per repetition: the slowest rank
     tl = np.sort(times.cpu().numpy())
     ms = float(np.median(tl))
@@ -389,6 +398,11 @@ def run_native(args, cfg):
         # every rank's own [sum, sum_sq, count] of the ring's steps, gathered; head must be their sum over the ranks
         c = chunk(ring)
         rings = [c] if overlap else c
+        for r_ in rings:  # one more pass over every slot, then drain the lagging sums
+            r_.run()
+        for r_ in rings:
+            r_.flush()
+        torch.cuda.synchronize()
         mine = torch.stack([s.stats[:3] for s in steps]).contiguous()
         allv = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allv, mine)
@@ -400,7 +414,7 @@ def run_native(args, cfg):
         if mode == "none":
             ok, ranks_ok = torch.equal(got, mine), True
         else:  # peer: summed in rank order => bit-identical; NCCL: its own (deterministic) order
-            ok = torch.equal(got, want) if mode == "peer" else torch.allclose(got, want, rtol=1e-6, atol=0)
+            ok = torch.equal(got, want) if mode.startswith("peer") else torch.allclose(got, want, rtol=1e-6, atol=0)
             ranks_ok = bool((head[:, 3] == world).all())  # column 3 counts the ranks summed
         st_ok = inbox is None or int(inbox.status.item()) == 0
         flag = torch.tensor([1.0 if (ok and ranks_ok and st_ok) else 0.0], device=dev)
@@ -617,6 +631,7 @@ def run_native(args, cfg):
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": cdict,
+                "rank_median_ms_per_step": rank_medians,
                 "reps": R, "ms_per_step_min": float(tl[0]) / K, "ms_per_step_p90": float(tl[int(0.9 * (R - 1))]) / K,
                 "timing": f"median over {R} repetitions of the {K}-step region (CUDA events per repetition, max over ranks per "
                           "repetition; ranks aligned on the device before each repetition)",
@@ -657,8 +672,8 @@ class _Slot:
     def __init__(self, inbox, i):
         self.inbox, self.i = inbox, i
 
-    def step_reduce(self, slot, head_ptr):
-        return self.inbox.step_reduce(self.i + slot, head_ptr)
+    def step_reduce(self, slot, head_ptr, **kw):
+        return self.inbox.step_reduce(self.i + slot, head_ptr, **kw)
 
 
 def _knn_group_only(L, s, st):
@@ -678,7 +693,7 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="one graph per step, no programmatic dependent launch")
     ap.add_argument("--reps", type=int, default=0, help="repetitions of the K-step timed region (0: enough for --min-region-ms, at least 25)")
     ap.add_argument("--min-region-ms", type=float, default=600.0, help="total timed time wanted (clock sampling needs a few hundred ms)")
-    ap.add_argument("--collective", default="auto", choices=["auto", "peer", "nccl", "none"],
+    ap.add_argument("--collective", default="auto", choices=["auto", "peer", "peer_sync", "peer_step", "nccl", "none"],
                     help="N > 1: per-step peer-memory all-reduce inside the loss launch (auto: if peer memory maps), or one NCCL all-reduce per graph")
     ap.add_argument("--no-checks", action="store_true", help="skip the oracle / all-reduce checks after the timed region")
     args = ap.parse_args()

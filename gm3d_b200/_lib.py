@@ -18,7 +18,8 @@ KNN_MAX_K = 32
 LOSS_STATS_LEN = 8
 STEP_OVERLAP_NEXT, STEP_OVERLAP_PREV, STEP_AFTER_PREV, STEP_SHARED_SMS = 1, 2, 4, 8
 MAX_PEERS = 8
-INBOX_BYTES = 2 * MAX_PEERS * 32
+INBOX_DEPTH = 4
+INBOX_BYTES = INBOX_DEPTH * MAX_PEERS * 32
 
 
 class StepReduce(ctypes.Structure):
@@ -26,7 +27,8 @@ class StepReduce(ctypes.Structure):
     {sum, sum_sq, count}.  Passed by HOST pointer; the library copies it into the kernel parameters."""
     _fields_ = [("head", ctypes.c_void_p), ("world", ctypes.c_int), ("rank", ctypes.c_int),
                 ("inbox", ctypes.c_void_p * MAX_PEERS), ("epoch", ctypes.c_void_p),
-                ("timeout_us", ctypes.c_uint), ("status", ctypes.c_void_p)]
+                ("timeout_us", ctypes.c_uint), ("defer", ctypes.c_int), ("status", ctypes.c_void_p),
+                ("collected", ctypes.c_void_p)]
 
 
 _vp, _i, _u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
@@ -54,6 +56,7 @@ SIGNATURES = {
     "gm3d_encoder_fwd_bf16": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "gm3d_cloud_step_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _u64, _u64, _vp, _vp, _vp,
                                  ctypes.c_float, ctypes.c_float, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "gm3d_step_reduce_collect": (_i, [_vp, _i, _vp]),
     "gm3d_peer_alloc": (_i, [ctypes.c_size_t, ctypes.POINTER(_vp), ctypes.c_char_p]),
     "gm3d_peer_open": (_i, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "gm3d_peer_close": (_i, [_vp]),

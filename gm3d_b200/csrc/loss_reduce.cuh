@@ -17,7 +17,29 @@ struct InboxSlot {
     float sum, sq, cnt, pad;
     unsigned flag, pad2[3];
 };
-static_assert(sizeof(InboxSlot) == 32 && GM3D_INBOX_BYTES == 2 * GM3D_MAX_PEERS * sizeof(InboxSlot), "inbox layout");
+static_assert(sizeof(InboxSlot) == 32 && GM3D_INBOX_BYTES == GM3D_INBOX_DEPTH * GM3D_MAX_PEERS * sizeof(InboxSlot), "inbox layout");
+static_assert((GM3D_INBOX_DEPTH & (GM3D_INBOX_DEPTH - 1)) == 0, "inbox depth");
+
+// Wait (bounded) until the slot's flag equals `epoch`, then read the contribution.  NaN marks one that never arrived.
+__device__ __forceinline__ bool inbox_wait(const InboxSlot* src, unsigned epoch, unsigned timeout_us, float& a, float& b,
+                                           float& c) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const unsigned long long limit = static_cast<unsigned long long>(timeout_us ? timeout_us : 2000000u) * 1000ull;
+    for (;;) {
+        unsigned f;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(&src->flag) : "memory");
+        if (f == epoch) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > limit) {
+            a = b = c = __int_as_float(0x7fc00000);
+            return false;
+        }
+    }
+    float pad;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(pad) : "l"(src) : "memory");
+    return true;
+}
 
 __device__ __forceinline__ void publish_step_stats(const gm3d_step_reduce_t& r, float sum, float sq, float cnt) {
     __shared__ float s_in[GM3D_MAX_PEERS][3];
@@ -39,32 +61,16 @@ __device__ __forceinline__ void publish_step_stats(const gm3d_step_reduce_t& r, 
     const float v0 = s_in[0][0], v1 = s_in[0][1], v2 = s_in[0][2];
     __syncthreads();
     if (tid < r.world) {
-        InboxSlot* dst = static_cast<InboxSlot*>(r.inbox[tid]) + (epoch & 1u) * GM3D_MAX_PEERS + r.rank;
+        InboxSlot* dst = static_cast<InboxSlot*>(r.inbox[tid]) + (epoch & (GM3D_INBOX_DEPTH - 1u)) * GM3D_MAX_PEERS + r.rank;
         asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v0), "f"(v1), "f"(v2), "f"(0.0f) : "memory");
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&dst->flag), "r"(epoch) : "memory");
+    }
+    if (r.defer) return;  // CTA-uniform: the sums are formed later by gm3d_step_reduce_collect
+    if (tid < r.world) {
         // wait for rank `tid`'s push of the same launch into the local inbox
-        const InboxSlot* src = static_cast<const InboxSlot*>(r.inbox[r.rank]) + (epoch & 1u) * GM3D_MAX_PEERS + tid;
-        unsigned long long t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        const unsigned long long limit = static_cast<unsigned long long>(r.timeout_us ? r.timeout_us : 2000000u) * 1000ull;
-        bool ok = true;
-        for (;;) {
-            unsigned f;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(&src->flag) : "memory");
-            if (f == epoch) break;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > limit) {
-                ok = false;
-                break;
-            }
-        }
-        float a = __int_as_float(0x7fc00000), b = a, c = a;  // NaN marks a contribution that never arrived
-        if (ok) {
-            float pad;
-            asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(pad) : "l"(src) : "memory");
-        } else {
-            atomicMax(&s_missing, tid + 1);
-        }
+        const InboxSlot* src = static_cast<const InboxSlot*>(r.inbox[r.rank]) + (epoch & (GM3D_INBOX_DEPTH - 1u)) * GM3D_MAX_PEERS + tid;
+        float a, b, c;
+        if (!inbox_wait(src, epoch, r.timeout_us, a, b, c)) atomicMax(&s_missing, tid + 1);
         s_in[tid][0] = a, s_in[tid][1] = b, s_in[tid][2] = c;
     }
     __syncthreads();

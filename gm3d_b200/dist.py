@@ -105,9 +105,12 @@ class PeerInbox:
                                ", ".join(f"rank {r}: {_lib.strerror(c)}" for r, c in bad))
         self.epoch = torch.zeros((self.slots,), dtype=torch.int32, device=self.dev)   # launch counter per slot
         self.status = torch.zeros((1,), dtype=torch.int32, device=self.dev)           # != 0: a peer never arrived
+        self.collected = torch.zeros((self.slots,), dtype=torch.int32, device=self.dev)  # launch count summed, per slot
         dist.barrier(group=group)  # every inbox is mapped everywhere before anybody pushes
 
-    def step_reduce(self, slot: int, head_ptr: int):
+    def step_reduce(self, slot: int, head_ptr: int, defer: bool = False, lag: bool = False):
+        """Descriptor of step slot `slot`.  defer: the loss launch only pushes (gm3d_step_reduce_collect sums);
+        lag: the collect may run beside the next replay's loss launches (it tracks `collected`)."""
         from . import _lib
         if not 0 <= slot < self.slots:
             raise IndexError(f"inbox slot {slot} out of range [0, {self.slots})")
@@ -117,6 +120,8 @@ class PeerInbox:
             r.inbox[q] = self.ptrs[q] + slot * _lib.INBOX_BYTES
         r.epoch = self.epoch.data_ptr() + 4 * slot
         r.timeout_us = self.timeout_us
+        r.defer = 1 if defer else 0
+        r.collected = self.collected.data_ptr() + 4 * slot if lag else None
         r.status = self.status.data_ptr()
         return r
 

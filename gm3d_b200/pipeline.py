@@ -224,8 +224,16 @@ class StepRing:
     reduce -- what happens to the [sum, sum_sq, count] head of every step's loss statistics (row i of `self.head`,
     (n, 4) f32, written by the tail of the step's loss launch; column 3 = number of ranks summed):
       'none'  this rank's values;
-      'peer'  summed over the ranks INSIDE the loss launch, per step, over peer memory (`inbox`: dist.PeerInbox) --
-              the reference's per-step all_reduce_mean (util/misc.py:345-353) without an NCCL launch or a host sync;
+      'peer'  per step over peer memory (`inbox`: dist.PeerInbox): the tail of every step's loss launch PUSHES this
+              rank's values into every rank's inbox over NVLink; one small launch per replay, forked at the START of
+              the graph, sums -- in rank order -- what all ranks pushed during the PREVIOUS replay while this replay
+              computes.  The reference's per-step all_reduce_mean (util/misc.py:345-353) without an NCCL launch or a
+              host sync, and no rank waits for another unless that one is a whole replay behind.  `head` therefore
+              lags one replay; flush() after the last replay brings it up to date;
+      'peer_sync'  as 'peer', but the sums of a replay are formed by a launch at the END of the same replay (no lag;
+              every replay ends with one wait for the slowest rank);
+      'peer_step'  as 'peer', but every loss launch itself waits for its step's pushes (the sum is in `head` the
+              moment that launch completes; the ranks then run in lock-step at step granularity);
       'nccl'  this rank's values, then ONE NCCL SUM all-reduce of the whole (n, 4) tensor at the end of the graph
               (batched: the reference reduces these scalars only to log them).
     Every rank must replay the ring the same number of times."""
@@ -240,9 +248,9 @@ class StepRing:
         self.schedule = schedule
         if reduce_stats is not None:  # round-1 spelling
             reduce = "nccl" if reduce_stats else "none"
-        if reduce not in ("none", "peer", "nccl"):
-            raise ValueError(f"reduce must be 'none', 'peer' or 'nccl', got {reduce!r}")
-        if reduce == "peer" and inbox is None:
+        if reduce not in ("none", "peer", "peer_sync", "peer_step", "nccl"):
+            raise ValueError(f"reduce must be 'none', 'peer', 'peer_sync', 'peer_step' or 'nccl', got {reduce!r}")
+        if reduce.startswith("peer") and inbox is None:
             raise ValueError("reduce='peer' needs a dist.PeerInbox with one slot per step")
         self.reduce = reduce
         self.inbox = inbox
@@ -251,8 +259,8 @@ class StepRing:
         self.head = torch.zeros((len(self.steps), 4), dtype=torch.float32, device=dev)
         self._red = []
         for i in range(len(self.steps)):
-            if reduce == "peer":
-                r = inbox.step_reduce(i, self.head[i].data_ptr())
+            if reduce.startswith("peer"):
+                r = inbox.step_reduce(i, self.head[i].data_ptr(), defer=reduce != "peer_step", lag=reduce == "peer")
             else:
                 r = _lib.StepReduce()
                 r.head, r.world, r.rank = self.head[i].data_ptr(), 1, 0
@@ -270,10 +278,33 @@ class StepRing:
     def _chain_flags(i, n):
         return (_lib.STEP_OVERLAP_NEXT if i + 1 < n else 0) | (_lib.STEP_OVERLAP_PREV if i > 0 else 0)
 
+    def _collect(self) -> None:
+        s0 = self.steps[0]
+        _lib.check("gm3d_step_reduce_collect", s0.lib.gm3d_step_reduce_collect(
+            ctypes.byref(self._red[0]), len(self.steps), torch.cuda.current_stream(s0.dev).cuda_stream))
+
+    def flush(self) -> None:
+        """reduce='peer': sum whatever the ranks have pushed and `head` does not hold yet (call after the last
+        replay, on every rank).  Enqueues on the current stream; no host sync."""
+        if self.reduce == "peer":
+            self._collect()
+            self._collect()
+
     def enqueue(self) -> None:
         n = len(self.steps)
         s0 = self.steps[0]
         main = torch.cuda.current_stream(s0.dev)
+        lag_join = None
+        if self.reduce == "peer":  # the previous replay's sums, beside this replay's launches
+            if self._side is None:
+                self._side = torch.cuda.Stream(s0.dev)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            self._side.wait_event(fork)
+            with torch.cuda.stream(self._side):
+                self._collect()
+                lag_join = torch.cuda.Event()
+                lag_join.record(self._side)
         nl = max(1, min(n, int(os.environ.get("GM3D_RING_LANES", "4"))))  # tuning aid; 1 = one stream
         if s0.fused and nl > 1 and 2 * s0.B <= FUSED_LANES_MAX_B and n >= 2 * nl:
             # Single-launch steps of small batches (one CTA per cloud fills a fraction of the 2 x 148 CTA slots):
@@ -352,7 +383,11 @@ class StepRing:
         else:
             for i, s in enumerate(self.steps):
                 s.enqueue(0, self._red[i])
-        if self.reduce == "nccl":
+        if lag_join is not None:
+            main.wait_event(lag_join)
+        if self.reduce == "peer_sync":
+            self._collect()
+        elif self.reduce == "nccl":
             import torch.distributed as dist
             dist.all_reduce(self.head)
 

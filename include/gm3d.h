@@ -109,11 +109,13 @@ extern "C" {
  * rank obtains bit-identical values).  A 12-byte message per step: latency-bound, no NCCL launch, no host work.
  *
  * Inbox of one rank for one step slot: GM3D_INBOX_BYTES bytes, zero before first use, laid out as
- * [parity 2][source rank GM3D_MAX_PEERS]{ f32 sum, sum_sq, count, pad; u32 flag; u32 pad[3] } -- the parity is
- * that of the slot's launch counter, so a fast peer's next launch never overwrites values still being read.
- * All ranks must launch every step slot the same number of times (a missing peer sets *status after timeout_us). */
+ * [launch count mod GM3D_INBOX_DEPTH][source rank GM3D_MAX_PEERS]{ f32 sum, sum_sq, count, pad; u32 flag; u32 pad[3] }
+ * -- a peer that runs ahead (at most two launches of the slot, see gm3d_step_reduce_collect) never overwrites values
+ * still being read.  All ranks must launch every step slot the same number of times (a missing peer sets *status
+ * after timeout_us). */
 #define GM3D_MAX_PEERS 8
-#define GM3D_INBOX_BYTES (2 * GM3D_MAX_PEERS * 32)
+#define GM3D_INBOX_DEPTH 4
+#define GM3D_INBOX_BYTES (GM3D_INBOX_DEPTH * GM3D_MAX_PEERS * 32)
 typedef struct gm3d_step_reduce {
     float* head;    /* 4 floats {sum, sum_sq, count, ranks summed} of this step (e.g. row i of a packed (steps,4)
                        tensor), or NULL.  world <= 1: this rank's own values. */
@@ -122,8 +124,26 @@ typedef struct gm3d_step_reduce {
     void* inbox[GM3D_MAX_PEERS]; /* inbox[r]: rank r's inbox for this step slot, mapped on THIS device (inbox[rank] is local) */
     unsigned* epoch;             /* this rank's launch counter of the step slot (device u32, zero before first use) */
     unsigned timeout_us;         /* bound of the wait for the peers; 0 = 2 s */
+    int defer;                   /* 0: the loss launch itself waits for the peers and writes the sum to `head`;
+                                    1: the loss launch only PUSHES (no launch ever waits for another rank); the sums
+                                       are formed later by gm3d_step_reduce_collect for a whole range of slots */
     int32_t* status;             /* device int32 or NULL: set to 1 + (first missing rank) when the wait timed out */
+    unsigned* collected;         /* gm3d_step_reduce_collect only: device u32 per slot (zero before first use) = launch
+                                    count already summed into `head`, or NULL (see there) */
 } gm3d_step_reduce_t;
+
+/* Deferred half of the exchange, for `n` CONSECUTIVE step slots in one small launch: slot i uses
+ * first->head + 4 i, first->inbox[r] + i * GM3D_INBOX_BYTES and first->epoch + i.  For every slot it waits until all
+ * ranks' pushes of the slot's CURRENT launch count have arrived, sums them in rank order and writes `head`.
+ * Enqueue it after the loss launches of the slots (e.g. once at the end of a graph of n steps): one wait per n steps
+ * instead of one per step, and no loss launch ever stalls on a slower rank.  n * world <= 1024.
+ * first->collected != NULL selects the LAGGING form, which may run BESIDE the loss launches of the same slots: for
+ * every slot it sums launch count collected[slot] + 1 -- if this rank has pushed that launch already, else the slot is
+ * skipped -- and advances collected[slot].  Enqueued at the start of every replay of a graph of steps it sums the
+ * PREVIOUS replay's pushes while the current replay computes: no rank ever waits for another unless that one is more
+ * than a whole replay behind (which also bounds how far ranks drift apart).  Two calls after the last replay drain
+ * whatever is still outstanding. */
+int gm3d_step_reduce_collect(const gm3d_step_reduce_t* first /* HOST */, int n, void* stream);
 
 /* HOST helpers (set-up time; they allocate and synchronise).  gm3d_peer_alloc: cudaMalloc + zero `bytes` on the
  * current device and export a 64-byte IPC handle; gm3d_peer_open maps another process's allocation into this

@@ -75,7 +75,7 @@ def test_argument_validation_returns_einval_without_a_device():
     red.world, red.rank = 2, 2
     assert lib.gm3d_chamfer_fused_f32(p, p, None, 4, 8, 8, 1.0, 1.0, None, None, None, None, None, None, None, 2, p, None,
                                       ctypes.byref(red), 0, p, None) == E
-    assert ctypes.sizeof(_lib.StepReduce) == 104 and _lib.INBOX_BYTES == 512
+    assert ctypes.sizeof(_lib.StepReduce) == 112 and _lib.INBOX_BYTES == 1024
     assert lib.gm3d_peer_alloc(0, None, None) == E and lib.gm3d_peer_open(None, None) == E
     with pytest.raises(ValueError):
         _lib.check("x", E)

@@ -850,6 +850,65 @@ def test_peer_reduce_two_ranks_on_one_gpu(cuda):
     assert status[0].item() == 2 and np.isnan(host(head[0, :3])).all()
 
 
+def test_peer_reduce_deferred_collect_on_one_gpu(cuda):
+    """Deferred form (defer = 1 + gm3d_step_reduce_collect): the loss launches of three step slots only push; one
+    collect launch per 'rank' sums all slots.  Both ranks on one GPU, two streams; two rounds (launch-counter parity)."""
+    import ctypes
+    from gm3d_b200 import _lib
+    from gm3d_b200.pipeline import GroupLossStep
+    lib = _lib.load()
+    B, N, G, k, n = 4, 256, 64, 8, 3
+    rng = np.random.default_rng(13)
+    inbox = torch.zeros((2, n, _lib.INBOX_BYTES), dtype=torch.uint8, device=cuda)
+    epoch = torch.zeros((2, n), dtype=torch.int32, device=cuda)
+    status = torch.zeros((2,), dtype=torch.int32, device=cuda)
+    head = torch.zeros((2, n, 4), dtype=torch.float32, device=cuda)
+    streams = [torch.cuda.Stream(cuda), torch.cuda.Stream(cuda)]
+    steps, reds = [[], []], [[], []]
+    for r in range(2):
+        for i in range(n):
+            s = GroupLossStep(B, N, G, k, 0.6, device=cuda, seed=r, rand_offset=i * B * G)
+            s.xyz.copy_(dev(synthetic_clouds(B, N, 70 + 10 * r + i), cuda))
+            s.loss_pred.copy_(dev(rng.standard_normal((B, G)).astype(np.float32), cuda))
+            s.pred.copy_(dev((rng.standard_normal((s.P, k, 3)) * 0.08).astype(np.float32), cuda))
+            red = _lib.StepReduce()
+            red.head, red.world, red.rank, red.defer = head[r, i].data_ptr(), 2, r, 1
+            red.inbox[0], red.inbox[1] = inbox[0, i].data_ptr(), inbox[1, i].data_ptr()
+            red.epoch, red.timeout_us, red.status = epoch[r, i:].data_ptr(), 500_000, status[r:].data_ptr()
+            steps[r].append(s)
+            reds[r].append(red)
+    torch.cuda.synchronize()
+    for it in range(2):
+        head.zero_()
+        for r in (0, 1):
+            with torch.cuda.stream(streams[r]):
+                for i in range(n):
+                    steps[r][i].enqueue(0, reds[r][i])
+                assert lib.gm3d_step_reduce_collect(ctypes.byref(reds[r][0]), n, streams[r].cuda_stream) == 0
+        torch.cuda.synchronize()
+        for i in range(n):
+            want = host(steps[0][i].stats[:3] + steps[1][i].stats[:3])
+            assert np.array_equal(host(head[0, i, :3]), want) and np.array_equal(host(head[1, i, :3]), want), (it, i)
+        assert (head[:, :, 3] == 2.0).all() and host(status).tolist() == [0, 0] and (epoch == it + 1).all()
+    # lagging form: `collected` starts at 0 while two launches have been pushed -- every call sums the next launch count
+    # (older pushes are still in the 4-deep inbox), a call with nothing outstanding leaves head alone
+    collected = torch.zeros((2, n), dtype=torch.int32, device=cuda)
+    for r in range(2):
+        reds[r][0].collected = collected[r].data_ptr()
+    for call in range(3):
+        head.zero_()
+        for r in (0, 1):
+            assert lib.gm3d_step_reduce_collect(ctypes.byref(reds[r][0]), n, streams[r].cuda_stream) == 0
+        torch.cuda.synchronize()
+        assert (collected == min(call + 1, 2)).all()
+        if call < 2:
+            for i in range(n):
+                want = host(steps[0][i].stats[:3] + steps[1][i].stats[:3])
+                assert np.array_equal(host(head[0, i, :3]), want) and np.array_equal(host(head[1, i, :3]), want)
+        else:
+            assert (head == 0).all()
+
+
 # ------------------------------------------------------------------------------------------ SURVEY 8(f) rows
 @pytest.fixture(scope="module")
 def golden_next():
