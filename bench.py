@@ -36,6 +36,8 @@ CONFIGS = {  # name: (B per GPU, N, G, k, mask_ratio, description)
     "c3l0": (128, 2048, 512, 16, 0.8, "Point-M2AE+GM3D level 0: B=128 N=2048 G=512 k=16 M=410"),
     "c3l1": (128, 512, 256, 8, 0.8, "Point-M2AE+GM3D level 1 (on level-0 centres): B=128 N=512 G=256 k=8 M=205"),
     "c3l2": (128, 256, 64, 8, 0.8, "Point-M2AE+GM3D level 2 (on level-1 centres): B=128 N=256 G=64 k=8 M=52"),
+    "c3": (128, 2048, (512, 256, 64), (16, 8, 8), 0.8, "Point-M2AE+GM3D hierarchy B=128 N=2048 G=512/256/64 k=16/8/8 (level l+1 groups "
+                                                        "level-l centres), M=410/205/52, multi-scale Chamfer-L2 fwd+bwd + hard-patch masks"),
     "c4": (32, 2048, 128, 32, 0.6, "ScanObjectNN finetune shape B=32 N=2048 G=128 k=32 (+loss for uniformity)"),
     "c5": (128, 8192, 512, 32, 0.6, "scaling sweep shard B=128/GPU N=8192 G=512 k=32 M=308"),
 }
@@ -108,10 +110,28 @@ def ring_size(B, N, G, k, M):
     return int(min(64, max(4, -(-2 * L2_BYTES // buffer_set_bytes(B, N, G, k, M)))))
 
 
+def m2ae_levels(cfg):
+    """[(N_l, G_l, k_l, M_l, len_keep, len_loss)] of a hierarchical config (G, k are tuples)."""
+    from gm3d_b200.masking import mask_lengths
+    B, N, Gs, ks, ratio, _ = cfg
+    out, n = [], N
+    for g, k in zip(Gs, ks):
+        len_keep, len_loss = mask_lengths(g, ratio, 199, 400)
+        out.append((n, g, k, g - len_keep, len_keep, len_loss))
+        n = g
+    return out
+
+
 def config_dict(cfg):
     """The workload description both arms print (identical keys and values => the driver's same_config check)."""
     from gm3d_b200.masking import mask_lengths
     B, N, G, k, ratio, desc = cfg
+    if isinstance(G, tuple):
+        lv = m2ae_levels(cfg)
+        per_set = sum(buffer_set_bytes(B, n, g, kk, m) for n, g, kk, m, _, _ in lv) - sum(B * n * 12 for n, *_ in lv[1:])
+        ring = int(min(64, max(4, -(-2 * L2_BYTES // per_set))))
+        return {"workload": desc, "B_per_gpu": B, "N": N, "G": list(G), "k": list(k), "M": [l[3] for l in lv],
+                "l2_policy": f"inputs larger than L2: ring of {ring} buffer sets x {per_set / 1e6:.1f} MB"}
     len_keep, _ = mask_lengths(G, ratio, 199, 400)
     M = G - len_keep
     ring = ring_size(B, N, G, k, M)
@@ -120,7 +140,7 @@ def config_dict(cfg):
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-def cpu_step(co, x, loss_pred, pred, G, k, len_keep, len_loss, rand_keys):
+def cpu_step(co, x, loss_pred, pred, G, k, len_keep, len_loss, rand_keys, want_center=False):
     """The same step with the CPU oracle (reference operator semantics)."""
     g = co.group(x, G, k)
     mask = co.hard_mask(loss_pred, len_keep, len_loss, rand_keys).astype(bool)
@@ -130,13 +150,62 @@ def cpu_step(co, x, loss_pred, pred, G, k, len_keep, len_loss, rand_keys):
     pp = co.chamfer_per_patch(d1, d2, 2)
     gd = np.full((P, k), 1.0 / (P * k), dtype=np.float32)
     ga, _ = co.chamfer_bwd(pred[:P], gt, i1, i2, gd, gd)
+    if want_center:
+        return float(pp.mean()), ga, g["center"]
     return float(pp.mean()), ga
+
+
+def m2ae_inputs(cfg, seed):
+    """Synthetic inputs of the hierarchy: the cloud, and per level the predicted losses and the predicted patches."""
+    B, N, Gs, ks, ratio, _ = cfg
+    x, _, _ = synthetic_batch(B, N, Gs[0], ks[0], 1, seed)
+    rng = np.random.default_rng(seed + 7)
+    lps = [rng.standard_normal((B, g)).astype(np.float32) for _, g, _, _, _, _ in m2ae_levels(cfg)]
+    preds = [(rng.standard_normal((B * m, k, 3)) * 0.08).astype(np.float32) for _, _, k, m, _, _ in m2ae_levels(cfg)]
+    return x, lps, preds
+
+
+def cpu_step_m2ae(co, cfg, x, lps, preds, rks):
+    cloud, loss = x, 0.0
+    for (n, g, k, m, len_keep, len_loss), lp, pred, rk in zip(m2ae_levels(cfg), lps, preds, rks):
+        loss_l, _, cloud = cpu_step(co, cloud, lp, pred, g, k, len_keep, len_loss, rk, want_center=True)  # next level: the centres
+        loss += loss_l
+    return loss
+
+
+def time_cpu_m2ae(cfg, budget_s: float, steps=None, warmup: int = 1):
+    from oracle import c_oracle as co
+    B = cfg[0]
+    x, lps, preds = m2ae_inputs(cfg, 1234)
+    lv = m2ae_levels(cfg)
+    rks = [np.random.default_rng(5 + i).random((B, l[1])).astype(np.float32) for i, l in enumerate(lv)]
+    sample_B = max(co.num_threads(), min(B, 16))
+    sub = lambda b: (x[:b], [a[:b] for a in lps], [p[: b * l[3]] for p, l in zip(preds, lv)], [r[:b] for r in rks])  # noqa: E731
+    t0 = time.perf_counter()
+    cpu_step_m2ae(co, cfg, *sub(sample_B))
+    one = time.perf_counter() - t0
+    if steps is None:
+        steps = max(2, min(50, int(budget_s / max(one, 1e-4))))
+    elif one * (steps + warmup) > budget_s:
+        sample_B = max(co.num_threads(), int(sample_B * budget_s / (one * (steps + warmup))))
+    args = sub(sample_B)
+    for _ in range(warmup):
+        cpu_step_m2ae(co, cfg, *args)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step_m2ae(co, cfg, *args)
+    dt = time.perf_counter() - t0
+    return {"value": sample_B * steps / dt, "unit": "clouds/s", "cores": co.num_threads(), "kind": "port",
+            "sample": f"{steps} steps x {sample_B} clouds of the {B}-cloud batch, three chained levels, C oracle on "
+                      f"{co.num_threads()} host threads, {dt:.1f} s"}, dt / steps
 
 
 def time_cpu(cfg, budget_s: float, steps=None, warmup: int = 1):
     """Time the oracle on a bounded sample: whole batches of `sample_B` clouds; returns clouds/s."""
     from oracle import c_oracle as co
     from gm3d_b200.masking import mask_lengths
+    if isinstance(cfg[2], tuple):
+        return time_cpu_m2ae(cfg, budget_s, steps, warmup)
     B, N, G, k, ratio, _ = cfg
     len_keep, len_loss = mask_lengths(G, ratio, 199, 400)
     M = G - len_keep
@@ -504,6 +573,40 @@ def run_native(args, cfg):
                               "grouping / mask; one GPU, this rank's share"}
             del sr, one
 
+    # ---- the same step through the DROP-IN operator surface, eagerly, the way the reference's training loop calls it:
+    # Group.forward -> generate_mask -> forward_loss -> backward (engine_pretrain_Classifier_SVM.py:108-118,176-184)
+    dropin = None
+    if rank == 0:
+        _stage("drop-in sequence")
+        from gm3d_b200 import loss as gl
+        from gm3d_b200 import masking
+        from gm3d_b200.group import Group
+        grp = Group(G, k)
+        s0 = steps[0]
+        predv = s0.pred.reshape(B, M, k * 3)
+
+        def dropin_step():
+            nb, _ = grp(s0.xyz)
+            mask = masking.generate_mask(s0.loss_pred, ratio, epoch=199, total_epoch=400, seed=1234, offset=0)
+            pr = predv.detach().requires_grad_(True)
+            out = gl.forward_loss_usual(pr, nb, mask)
+            out["Chamfer_mean"].backward()
+            return out["Chamfer_mean"], pr.grad
+        for _ in range(5):
+            dropin_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        nd = 50
+        for _ in range(nd):
+            lossv, gradv = dropin_step()
+        torch.cuda.synchronize()
+        td = (time.perf_counter() - t0) / nd
+        same = bool(torch.equal(gradv.reshape(s0.P, k, 3), s0.grad_pred)) and bool(torch.equal(lossv, s0.total.reshape(())))
+        dropin = {"value": B / td, "unit": "clouds/s", "ms_per_step": td * 1e3,
+                  "equals_step_outputs": same,
+                  "note": "eager Python: Group -> generate_mask -> forward_loss_usual (one fused fwd+bwd launch behind "
+                          "autograd) -> backward, allocations and host launch latency included; one GPU, this rank's share"}
+
     _stage("e2e")
     # ---- end-to-end: every step fed from pinned host memory, results read back
     # NGROUP graphs in flight on NGROUP streams, each = SUB x [H2D copy, the step, D2H copy]
@@ -647,7 +750,7 @@ def run_native(args, cfg):
                              "frac": step_bytes / (us_step * 1e-6) / 1e9 / hbm_peak},
                 "step_fp32": {"flop_per_step": step_flop, "tflops": step_flop / (us_step * 1e-6) / 1e12,
                               "frac": step_flop / (us_step * 1e-6) / 1e12 / fp32_peak},
-                "single_launch": single,
+                "single_launch": single, "dropin": dropin,
                 "cpu_baseline": cpu_base, "loss_check": loss_last, "parity_check": parity, "allreduce_check": allreduce}
         print(json.dumps(line), flush=True)
     failed = (parity is not None and parity != "ok") or (allreduce is not None and allreduce != "ok")
@@ -663,6 +766,147 @@ def run_native(args, cfg):
         sys.stderr.flush()
         os._exit(1 if failed else 0)
     if failed:
+        raise SystemExit(1)
+
+
+def run_c3(args, cfg):
+    """BASELINE config[2]: the three chained Point-M2AE grouping levels + masks + multi-scale Chamfer as ONE step."""
+    import torch
+
+    from gm3d_b200 import _lib
+    from gm3d_b200.pipeline import HostStagedGroup, HostStagedM2AE, M2AEStep, StepRing
+
+    _lib.load()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the gm3d_b200 path has no CPU fallback")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("bench.py --config c3 is a one-GPU configuration")
+    wd = _watchdog(float(os.environ.get("GM3D_BENCH_WATCHDOG_S", "540")))
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    B, N, Gs, ks, ratio, desc = cfg
+    K, W = args.steps, max(args.warmup, 3)
+    cdict = config_dict(cfg)
+    ring = int(cdict["l2_policy"].split("ring of ")[1].split()[0])
+    lv = m2ae_levels(cfg)
+
+    def fill(s, seed, host=False):
+        x, lps, preds = m2ae_inputs(cfg, seed)
+        if host:
+            s.h_views[0][0].copy_(torch.from_numpy(x))
+            for li in range(len(lv)):
+                v = s.h_views[li]
+                v[-2].copy_(torch.from_numpy(preds[li])); v[-1].copy_(torch.from_numpy(lps[li]))
+        else:
+            s.xyz.copy_(torch.from_numpy(x))
+            for l, lp, pr in zip(s.levels, lps, preds):
+                l.loss_pred.copy_(torch.from_numpy(lp)); l.pred.copy_(torch.from_numpy(pr))
+        return x, lps, preds
+
+    steps, first = [], None
+    for r in range(ring):
+        s = M2AEStep(B, N, Gs, ks, ratio, device=dev, seed=1234, rand_offset=r * B * Gs[0])
+        inp = fill(s, 1234 + r)
+        first = first or inp
+        steps.append(s)
+    chunks = {}
+
+    def run_steps(n):
+        for m in [ring] * (n // ring) + ([n % ring] if n % ring else []):
+            if m not in chunks:
+                chunks[m] = StepRing(steps[:m]).capture()
+            chunks[m].run()
+
+    run_steps(max(W, ring)); run_steps(K)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); run_steps(K); e1.record()
+    torch.cuda.synchronize()
+    R = args.reps if args.reps > 0 else int(min(3000, max(25, -(-args.min_region_ms // max(e0.elapsed_time(e1), 1e-3)))))
+    clocks = ClockSampler(0)
+    clocks.start()
+    time.sleep(0.15)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(R)]
+    torch.cuda.synchronize()
+    for a, b in ev:
+        a.record(); run_steps(K); b.record()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    tl = np.sort(np.array([a.elapsed_time(b) for a, b in ev]))
+    ms = float(np.median(tl))
+    # parity: every level of slot 0 against the oracle chain (level l+1 on the oracle's level-l centres)
+    parity = None
+    if not args.no_checks:
+        from oracle import c_oracle as co
+        try:
+            cloud = first[0]
+            for l, lp, pr in zip(steps[0].levels, first[1], first[2]):
+                oracle_check_step(l, cloud, lp, pr)
+                cloud = co.group(cloud, l.G, l.k)["center"]
+            parity = "ok"
+        except AssertionError as e:
+            parity = f"FAILED: {e}"
+    # e2e: host-fed steps, a few graphs in flight
+    NG, SUB = 4, 2
+    groups = []
+    for gi in range(NG):
+        sub = []
+        for r in range(SUB):
+            s = HostStagedM2AE(B, N, Gs, ks, ratio, device=dev, seed=1234, rand_offset=(gi * SUB + r) * B * Gs[0])
+            fill(s, 4321 + gi * SUB + r, host=True)
+            sub.append(s)
+        groups.append(HostStagedGroup(sub).capture())
+    Ke = -(-max(K, 64) // SUB) * SUB
+    losses = []
+
+    def e2e(n):
+        busy = [False] * NG
+        for i in range(n // SUB):
+            j = i % NG
+            if busy[j]:
+                losses.extend(groups[j].losses())
+            groups[j].launch(); busy[j] = True
+        for j in range(NG):
+            if busy[j]:
+                losses.extend(groups[j].losses())
+    e2e(NG * SUB * 2)
+    torch.cuda.synchronize(); losses.clear()
+    t0 = time.perf_counter(); e2e(Ke); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    hs = groups[0].steps[0]
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    fp32_peak = 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
+    us = ms / K * 1e3
+    sb, sf = steps[0].step_bytes_per_cloud() * B, steps[0].flop_per_cloud() * B
+    hbm_gbs, fp32_tf = sb / (us * 1e-6) / 1e9, sf / (us * 1e-6) / 1e12
+    by_fp32 = fp32_tf / fp32_peak > hbm_gbs / hbm_peak
+    cpu_base, _ = time_cpu(cfg, budget_s=12.0) if not args.no_cpu_baseline else ({"value": None, "unit": "clouds/s", "cores": 0, "kind": "port", "sample": "skipped"}, 0)
+    line = {"metric": METRIC, "value": B * K / (ms * 1e-3), "unit": "clouds/s", "n_gpus": 1, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": cdict, "reps": R, "ms_per_step_min": float(tl[0]) / K,
+            "ms_per_step_p90": float(tl[int(0.9 * (R - 1))]) / K,
+            "run": {"path": "dataflow", "kernels_per_step": steps[0].kernels_per_step, "cuda_graph": True,
+                    "step_overlap": f"independent steps round-robin on forked streams inside graphs of up to {ring} steps",
+                    "collective": "none"},
+            "clocks": clk,
+            "e2e": {"value": B * Ke / dt, "unit": "clouds/s", "h2d_bytes_per_step": hs.h2d_bytes, "d2h_bytes_per_step": hs.d2h_bytes,
+                    "ms_per_step": dt / Ke * 1e3, "steps": Ke, "losses_read": len(losses)},
+            "gpu_launches": steps[0].kernels_per_step * K,
+            "roofline": {"kernel": f"m2ae step ({steps[0].kernels_per_step} launches)", "bound": "fp32" if by_fp32 else "hbm",
+                         "achieved": fp32_tf if by_fp32 else hbm_gbs, "peak": fp32_peak if by_fp32 else hbm_peak,
+                         "unit": "TFLOP/s" if by_fp32 else "GB/s", "frac": (fp32_tf / fp32_peak) if by_fp32 else hbm_gbs / hbm_peak,
+                         "traffic": None, "peak_source": peak_src, "hbm_gbs": hbm_gbs, "hbm_frac": hbm_gbs / hbm_peak,
+                         "fp32_tflops": fp32_tf, "fp32_frac": fp32_tf / fp32_peak, "us_per_launch": us,
+                         "algorithmic_bytes_per_launch": sb, "algorithmic_flop_per_launch": sf},
+            "cpu_baseline": cpu_base, "loss_check": losses[-1] if losses else None, "parity_check": parity}
+    print(json.dumps(line), flush=True)
+    wd.cancel()
+    if parity is not None and parity != "ok":
         raise SystemExit(1)
 
 
@@ -700,6 +944,8 @@ def main():
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
         run_reference(args, cfg)
+    elif isinstance(cfg[2], tuple):
+        run_c3(args, cfg)
     else:
         run_native(args, cfg)
 

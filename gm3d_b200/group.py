@@ -47,3 +47,29 @@ class GroupGM3D(Group):
 
     def __init__(self, num_group: int, group_size: int):
         super().__init__(num_group, group_size, return_org=True)
+
+
+class GroupM2AE(nn.Module):
+    """The hierarchical grouping of Point-M2AE(+GM3D): `Group` levels chained on the previous level's centres
+    (/root/reference/Point-M2AE_SA3D/cfgs/config_Point_M2AE.yaml:57-69 -- num_groups [512, 256, 64], group_sizes
+    [16, 8, 8]; fine-tune: sizes [32, 16, 16], config_finetune_scan_hardest_PointM2AE.yaml:58-69).  The model code
+    of Point-M2AE+GM3D is not in the reference tree; the chaining rule is Point-M2AE's published one:
+    level 0 groups the raw cloud, level l > 0 groups centres[l-1].
+        forward(xyz (B,N,3)) -> (neighborhoods [ (B,G_l,k_l,3) ], centers [ (B,G_l,3) ], idxs [ (B,G_l,k_l) int64 ])
+    idxs[l] index into level l's input cloud (xyz for l = 0, centers[l-1] otherwise)."""
+
+    def __init__(self, num_groups=(512, 256, 64), group_sizes=(16, 8, 8)):
+        super().__init__()
+        self.num_groups, self.group_sizes = tuple(num_groups), tuple(group_sizes)
+
+    @torch.no_grad()
+    def forward(self, xyz):
+        neighborhoods, centers, idxs = [], [], []
+        cloud = xyz
+        for g, k in zip(self.num_groups, self.group_sizes):
+            r = ops.group(cloud.float().contiguous(), g, k, want_idx=True)
+            neighborhoods.append(r["neighborhood"])
+            centers.append(r["center"])
+            idxs.append(r["knn_idx"])
+            cloud = r["center"]
+        return neighborhoods, centers, idxs

@@ -38,9 +38,12 @@ FUSED_MAX_N, FUSED_MAX_G = 2048, 1024  # gm3d_cloud_step_f32 serves these; large
 class GroupLossStep:
     def __init__(self, B: int, N: int, G: int, k: int, mask_ratio: float = 0.6, epoch: int = 199,
                  total_epoch: int = 400, ratio_cap: float = 0.8, norm: int = 2, device=None, seed: int = 0,
-                 rand_offset: int = 0, fused: Optional[bool] = None, path: Optional[str] = None):
+                 rand_offset: int = 0, fused: Optional[bool] = None, path: Optional[str] = None,
+                 xyz: Optional[torch.Tensor] = None):
         """path: 'dataflow' (default: group -> mask -> Chamfer launches) or 'single' (one gm3d_cloud_step_f32 launch;
-        `fused=True` is the same request, `fused=False` forces the dataflow path with separate fps / kNN kernels)."""
+        `fused=True` is the same request, `fused=False` forces the dataflow path with separate fps / kNN kernels).
+        xyz: use this (B,N,3) tensor as the input cloud instead of allocating one (a hierarchy level that groups the
+        previous level's centres: M2AEStep)."""
         self.lib = _lib.load()
         can_fuse = N <= FUSED_MAX_N and G <= FUSED_MAX_G and k <= _lib.KNN_MAX_K
         if path is None:
@@ -81,9 +84,17 @@ class GroupLossStep:
             return sum(((int(torch.tensor(sh).prod().item()) * torch.empty((), dtype=dt).element_size()) + 255) & ~255
                        for sh, dt in specs)
 
-        self._in_specs = [((B, N, 3), f32), ((self.P, k, 3), f32), ((B, G), f32)]
-        self.in_arena = e((arena_bytes(self._in_specs),), torch.uint8)
-        self.xyz, self.pred, self.loss_pred = carve(self.in_arena, self._in_specs)
+        if xyz is None:
+            self._in_specs = [((B, N, 3), f32), ((self.P, k, 3), f32), ((B, G), f32)]
+            self.in_arena = e((arena_bytes(self._in_specs),), torch.uint8)
+            self.xyz, self.pred, self.loss_pred = carve(self.in_arena, self._in_specs)
+        else:
+            if tuple(xyz.shape) != (B, N, 3) or xyz.dtype != f32 or not xyz.is_contiguous() or xyz.device != d:
+                raise ValueError(f"xyz must be a contiguous float32 ({B},{N},3) tensor on {d}")
+            self._in_specs = [((self.P, k, 3), f32), ((B, G), f32)]
+            self.in_arena = e((arena_bytes(self._in_specs),), torch.uint8)
+            self.pred, self.loss_pred = carve(self.in_arena, self._in_specs)
+            self.xyz = xyz
         # results a host reads back every step: one arena [stats | per_patch | mask] = ONE D2H copy
         self._res_specs = [((_lib.LOSS_STATS_LEN,), f32), ((self.P,), f32), ((B, G), torch.uint8)]
         self.res_arena = e((arena_bytes(self._res_specs),), torch.uint8)
@@ -213,6 +224,64 @@ class GroupLossStep:
             self.graph.replay()
         else:
             self.enqueue()
+
+
+class M2AEStep:
+    """One step of the Point-M2AE+GM3D hierarchy (BASELINE config[2];
+    /root/reference/Point-M2AE_SA3D/cfgs/config_Point_M2AE.yaml:57-69: num_groups 512/256/64, group_sizes 16/8/8,
+    mask_ratio 0.8): three chained Group levels -- level 0 groups the raw cloud, level l+1 groups the CENTRES of
+    level l -- and per level the hard-patch mask (M_l = G_l - int(G_l (1 - ratio))) and Chamfer-L2 forward + backward
+    of the masked patches against a prediction.  Level l+1's input cloud IS level l's `center` tensor (no copy).
+    Quacks like a GroupLossStep for StepRing (kernel-sequence lanes) and HostStagedGroup."""
+
+    fused = False
+    group_per_cloud = False
+    path = "dataflow"
+
+    def __init__(self, B: int, N: int, groups=(512, 256, 64), sizes=(16, 8, 8), mask_ratio: float = 0.8, device=None,
+                 seed: int = 0, rand_offset: int = 0, **kw):
+        self.B, self.N = B, N
+        self.levels: List[GroupLossStep] = []
+        n, xyz = N, None
+        for li, (g, k) in enumerate(zip(groups, sizes)):
+            s = GroupLossStep(B, n, g, k, mask_ratio, device=device, seed=seed + li, rand_offset=rand_offset, xyz=xyz, **kw)
+            self.levels.append(s)
+            n, xyz = g, s.center
+        self.dev, self.lib = self.levels[0].dev, self.levels[0].lib
+        self.kernels_per_step = sum(s.kernels_per_step for s in self.levels)
+        self.stats = self.levels[0].stats  # StepRing publishes level 0's statistics head
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+
+    @property
+    def xyz(self):
+        return self.levels[0].xyz
+
+    def step_bytes_per_cloud(self) -> int:
+        return sum(s.step_bytes_per_cloud() for s in self.levels)
+
+    def flop_per_cloud(self) -> int:
+        return sum(8 * ((s.G - 1) * s.N + s.G * s.N + s.M * s.k * s.k) for s in self.levels)
+
+    def enqueue(self, flags: int = 0, reduce: Optional[_lib.StepReduce] = None) -> None:
+        """masks (they need loss_pred only) on a forked stream; the three group launches in order (level l+1 reads
+        level l's centres); then the three Chamfer launches."""
+        main = torch.cuda.current_stream(self.dev)
+        side = self.levels[0].side
+        fork, join = torch.cuda.Event(), torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            for s in self.levels:
+                s.enqueue_mask()
+        join.record(side)
+        for s in self.levels:
+            s.enqueue_group(0)
+        main.wait_event(join)
+        for li, s in enumerate(self.levels):
+            s.enqueue_loss(reduce if li == 0 else None)
+
+    capture = GroupLossStep.capture
+    run = GroupLossStep.run
 
 
 class StepRing:
@@ -445,6 +514,34 @@ class HostStagedStep(GroupLossStep):
             self.in_arena.copy_(self.h_in, non_blocking=True)
         super().enqueue(flags, reduce)
         self.h_res.copy_(self.res_arena, non_blocking=True)
+
+
+class HostStagedM2AE(M2AEStep):
+    """M2AEStep fed from / drained to pinned host memory: per step ONE H2D copy per level (level 0: cloud + prediction
+    + predicted losses; levels 1, 2: prediction + predicted losses -- their clouds are the previous level's centres)
+    and ONE D2H copy per level (statistics, per-patch losses, mask)."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.h_in = [torch.empty(s.in_arena.shape, dtype=torch.uint8, pin_memory=True) for s in self.levels]
+        self.h_res = [torch.empty(s.res_arena.shape, dtype=torch.uint8, pin_memory=True) for s in self.levels]
+        self.h_views = [s._carve(h, s._in_specs) for s, h in zip(self.levels, self.h_in)]  # level 0: xyz, pred, loss_pred
+        self.h_stats = self.levels[0]._carve(self.h_res[0], self.levels[0]._res_specs)[0]
+
+    @property
+    def h2d_bytes(self) -> int:
+        return sum(h.numel() for h in self.h_in)
+
+    @property
+    def d2h_bytes(self) -> int:
+        return sum(h.numel() for h in self.h_res)
+
+    def enqueue(self, flags: int = 0, reduce: Optional[_lib.StepReduce] = None) -> None:
+        for s, h in zip(self.levels, self.h_in):
+            s.in_arena.copy_(h, non_blocking=True)
+        super().enqueue(flags, reduce)
+        for s, h in zip(self.levels, self.h_res):
+            h.copy_(s.res_arena, non_blocking=True)
 
 
 class HostStagedGroup:

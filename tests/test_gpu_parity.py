@@ -807,6 +807,42 @@ def test_step_ring_bench_variant_every_slot_vs_oracle(cuda, path):
         assert np.array_equal(host(ring.head[i, :3]), host(s.stats[:3]))
 
 
+def test_m2ae_chain_vs_oracle_chain(cuda):
+    """BASELINE config[2] as ONE step: three chained Group levels (level l+1 groups the centres of level l), masks
+    and multi-scale Chamfer -- every level against the oracle chain, the GroupM2AE module against the same chain,
+    and a ring of steps against the steps run alone."""
+    import bench
+    from gm3d_b200.group import GroupM2AE
+    from gm3d_b200.pipeline import M2AEStep, StepRing
+    cfg = (6,) + bench.CONFIGS["c3"][1:]
+    B, N, Gs, ks, ratio, _ = cfg
+    steps, inputs = [], []
+    for r in range(3):
+        s = M2AEStep(B, N, Gs, ks, ratio, device=cuda, seed=3, rand_offset=r * B * Gs[0])
+        x, lps, preds = bench.m2ae_inputs(cfg, 50 + r)
+        s.xyz.copy_(dev(x, cuda))
+        for l, lp, pr in zip(s.levels, lps, preds):
+            l.loss_pred.copy_(dev(lp, cuda)); l.pred.copy_(dev(pr, cuda))
+        steps.append(s)
+        inputs.append((x, lps, preds))
+    assert steps[0].levels[1].xyz.data_ptr() == steps[0].levels[0].center.data_ptr()  # chained without a copy
+    ring = StepRing(steps).capture()
+    ring.run(); ring.run()
+    torch.cuda.synchronize()
+    for s, (x, lps, preds) in zip(steps, inputs):
+        cloud = x
+        for l, lp, pr in zip(s.levels, lps, preds):
+            assert bench.oracle_check_step(l, cloud, lp, pr) == "ok"
+            cloud = co.group(cloud, l.G, l.k)["center"]
+    nbs, cs, idxs = GroupM2AE(Gs, ks)(steps[0].xyz)
+    cloud = inputs[0][0]
+    for l, nb, c, idx, g, k in zip(steps[0].levels, nbs, cs, idxs, Gs, ks):
+        w = co.group(cloud, g, k)
+        assert torch.equal(nb, l.neighborhood) and torch.equal(c, l.center)
+        assert np.array_equal(host(idx), w["knn_idx"]) and idx.dtype == torch.int64
+        cloud = w["center"]
+
+
 def test_peer_reduce_two_ranks_on_one_gpu(cuda):
     """The per-step statistics all-reduce over peer memory (gm3d_step_reduce_t), with both 'ranks' played by two
     streams of ONE GPU sharing two local inboxes: each rank's head must hold rank0 + rank1 (summed in rank order, so
