@@ -22,7 +22,7 @@ struct ChamferWarpScratch {  // per warp, 16-byte aligned
     float4 bxy[16];          // {x_2p, x_2p+1, y_2p, y_2p+1}
     float2 bz[16];           // {z_2p, z_2p+1}
     float4 bg[32];           // {x_j, y_j, z_j, 2 * upstream gradient of dist2[j]}: one LDS.128 per scatter source
-    uint2 col[32];           // direction 2: {minimum bits, ballot of the lanes holding it} of column j
+    unsigned col[32];        // direction 2: ballot of the lanes holding the minimum of column j
     unsigned in[32];         // incoming-source masks of the backward
 };
 
@@ -53,8 +53,11 @@ __device__ __forceinline__ ChamferWarpOut chamfer_patch_warp(float ax, float ay,
     }
     __syncwarp();
     const float2 ax2 = make_float2(ax, ax), ay2 = make_float2(ay, ay), az2 = make_float2(az, az);
-    float D[32];
-    float best1 = inf;
+    // Squared distances are >= 0 (or +inf / NaN in padding lanes), so their bit patterns order like unsigned integers:
+    // the running minimum is one VIMNMX that also says which side won (ties keep the earlier index, as upstream's
+    // strict `<` does) + one select for the index.
+    unsigned D[32];
+    unsigned bestb = 0xffffffffu;
     int besti1 = 0;
 #pragma unroll
     for (int p = 0; p < 16; ++p) {
@@ -62,23 +65,30 @@ __device__ __forceinline__ ChamferWarpOut chamfer_patch_warp(float ax, float ay,
         const float2 z = sc->bz[p];
         // upstream evaluates x = other - mine; first minimum wins (strict <), committed in index order
         const float2 d = sumsq_nvcc2(sub2(make_float2(xy.x, xy.y), ax2), sub2(make_float2(xy.z, xy.w), ay2), sub2(z, az2));
-        D[2 * p] = d.x, D[2 * p + 1] = d.y;
-        if (d.x < best1) best1 = d.x, besti1 = 2 * p;
-        if (d.y < best1) best1 = d.y, besti1 = 2 * p + 1;
+        D[2 * p] = __float_as_uint(d.x), D[2 * p + 1] = __float_as_uint(d.y);
+        bool keep;
+        bestb = __vibmin_u32(bestb, D[2 * p], &keep);
+        besti1 = keep ? besti1 : 2 * p;
+        bestb = __vibmin_u32(bestb, D[2 * p + 1], &keep);
+        besti1 = keep ? besti1 : 2 * p + 1;
     }
-    // direction 2: column minima over the lanes.  The REDUX result and the ballot are warp-uniform; one lane
-    // parks them in shared memory and lane j picks column j up afterwards (no per-column selects).
+    const float best1 = __uint_as_float(bestb);
+    // direction 2: column minima over the lanes.  The REDUX result is warp-uniform; the ballot of the lanes that hold
+    // it is parked in shared memory by one lane and lane j picks column j up afterwards (no per-column selects).  The
+    // minimum itself is re-evaluated by lane j from its arg-min (same expression => same bits).
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        const unsigned bits = __float_as_uint(D[j]);
-        const unsigned mn = __reduce_min_sync(kFull, bits);
-        const unsigned bal = __ballot_sync(kFull, bits == mn);
-        if (lane == 0) sc->col[j] = make_uint2(mn, bal);
+        const unsigned mn = __reduce_min_sync(kFull, D[j]);
+        const unsigned bal = __ballot_sync(kFull, D[j] == mn);
+        if (lane == 0) sc->col[j] = bal;
     }
     __syncwarp();
-    const uint2 cj = sc->col[lane];
-    const float best2 = __uint_as_float(cj.x);
-    const int besti2 = __ffs(cj.y) - 1;  // lowest lane = upstream's first minimum
+    const int besti2 = __ffs(sc->col[lane]) - 1;  // lowest lane = upstream's first minimum
+    float best2;
+    {
+        const float qx = __shfl_sync(kFull, ax, besti2), qy = __shfl_sync(kFull, ay, besti2), qz = __shfl_sync(kFull, az, besti2);
+        best2 = sumsq_nvcc(__fsub_rn(bx, qx), __fsub_rn(by, qy), __fsub_rn(bz, qz));
+    }
     ChamferWarpOut o;
     o.dist1 = best1, o.dist2 = best2, o.idx1 = besti1, o.idx2 = besti2;
     const float f1 = live ? (norm == 1 ? __fsqrt_rn(best1) : best1) : 0.0f;

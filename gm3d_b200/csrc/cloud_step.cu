@@ -34,6 +34,10 @@ namespace gm3d {
 
 constexpr int kCsMaxFpsWarps = 8;
 
+struct CloudStepSmem {  // offsets into dynamic shared memory (computed once on the host, carried in the parameters)
+    unsigned sx, sy, sz, aos, sel, ready, cand, cham, key, msel, mrank, total;
+};
+
 struct CloudStepParams {
     const float* xyz;
     int B, N, G, k;
@@ -64,18 +68,16 @@ struct CloudStepParams {
     int LP;    // G rounded up to a power of two (>= 64)
     int has_red;
     gm3d_step_reduce_t red;  // statistics publish / peer all-reduce in the tail (has_red)
+    CloudStepSmem L;         // shared-memory layout of this launch
 };
 
-struct CloudStepSmem {  // offsets into dynamic shared memory
-    size_t sx, sy, sz, aos, sel, ready, cand, cham, key, msel, mrank, total;
-};
 
-__host__ __device__ inline CloudStepSmem cloud_step_layout(int N, int G, int npad, int LP, int warps, bool loss) {
+inline CloudStepSmem cloud_step_layout(int N, int G, int npad, int LP, int warps, bool loss) {
     CloudStepSmem L;
-    size_t o = 0;
+    unsigned o = 0;
     auto take = [&](size_t bytes) {
-        const size_t at = o;
-        o += (bytes + 15) & ~static_cast<size_t>(15);
+        const unsigned at = o;
+        o += static_cast<unsigned>((bytes + 15) & ~static_cast<size_t>(15));
         return at;
     };
     L.sx = take(static_cast<size_t>(npad) * 4);
@@ -127,7 +129,7 @@ __device__ __forceinline__ void cloud_step_body(const CloudStepParams& p) {
     // this launch's buffers, so it may start filling SMs as soon as every CTA of this grid is resident.
     pdl_enter(p.flags);
     const int N = p.N, G = p.G, k = p.k;
-    const CloudStepSmem L = cloud_step_layout(N, G, p.npad, p.LP, WARPS, LOSS);
+    const CloudStepSmem& L = p.L;
     float* sx = reinterpret_cast<float*>(smem_raw + L.sx);
     float* sy = reinterpret_cast<float*>(smem_raw + L.sy);
     float* sz = reinterpret_cast<float*>(smem_raw + L.sz);
@@ -222,15 +224,16 @@ __device__ __forceinline__ void cloud_step_body(const CloudStepParams& p) {
             const float* w = s_aos + 3 * old;  // winner of the previous round (AoS copy: one address, three loads)
             const float x1 = w[0], y1 = w[1], z1 = w[2];
             const float2 x2 = make_float2(x1, x1), y2 = make_float2(y1, y1), z2 = make_float2(z1, z1);
-            float m[PPT];
+            int m[PPT];  // running-min distances as order-preserving integers (values are -1 or >= 0)
 #pragma unroll
             for (int h = 0; h < PPT / 2; ++h) {
                 const float2 d = sumsq_nvcc2(sub2(X[h], x2), sub2(Y[h], y2), sub2(Z[h], z2));
                 T[h].x = fminf(d.x, T[h].x);
                 T[h].y = fminf(d.y, T[h].y);
-                m[2 * h] = T[h].x, m[2 * h + 1] = T[h].y;
+                m[2 * h] = f2ord(T[h].x), m[2 * h + 1] = f2ord(T[h].y);
             }
-            // thread arg-max, lowest slot on ties (slot s <-> point s * FT + tid): pairwise tournament
+            // thread arg-max, lowest slot on ties (slot s <-> point s * FT + tid): pairwise tournament; VIMNMX returns the
+            // maximum AND which side won (lower slot >= upper slot keeps the lower one) in one instruction
             int mi[PPT];
 #pragma unroll
             for (int s = 0; s < PPT; ++s) mi[s] = s;
@@ -238,12 +241,12 @@ __device__ __forceinline__ void cloud_step_body(const CloudStepParams& p) {
             for (int ww = 1; ww < PPT; ww <<= 1) {
 #pragma unroll
                 for (int s = 0; s < PPT; s += 2 * ww) {
-                    const bool hi = m[s + ww] > m[s];
-                    m[s] = hi ? m[s + ww] : m[s];
-                    mi[s] = hi ? mi[s + ww] : mi[s];
+                    bool lo;
+                    m[s] = __vibmax_s32(m[s], m[s + ww], &lo);
+                    mi[s] = lo ? mi[s] : mi[s + ww];
                 }
             }
-            const int v = f2ord(m[0]);
+            const int v = m[0];
             const int besti = mi[0] * kCsFpsThreads + ftid;
             const int vmax = __reduce_max_sync(kFull, v);
             const int kmin = __reduce_min_sync(kFull, v == vmax ? besti : INT_MAX);
@@ -352,9 +355,10 @@ __device__ __forceinline__ void cloud_step_body(const CloudStepParams& p) {
     };
     if (dbg_mode != 1 && dbg_mode != 3) {
         if constexpr (DYNAMIC) {
+            const uint32_t next_addr = smem_u32(&s_next);
             for (;;) {
                 int g = 0;
-                if (lane == 0) g = atomicAdd(&s_next, 1);
+                if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(g) : "r"(next_addr) : "memory");
                 g = __shfl_sync(kFull, g, 0);
                 if (g >= G) break;
                 process_patch(g);
@@ -436,6 +440,7 @@ template <int WARPS>
 static int cloud_step_dispatch(CloudStepParams& p, bool loss, cudaStream_t st) {
     const CloudStepSmem L = cloud_step_layout(p.N, p.G, p.npad, p.LP, WARPS, loss);
     if (L.total > 200 * 1024) return GM3D_ENOSUP;
+    p.L = L;
     // N <= 1024: four sampler warps (one per SM sub-partition) with 8 points per thread -- half the issue slots
     // of eight warps x 4 points for the same chain, and four more workers; else eight sampler warps x 8 points
     if (p.N <= 1024) {

@@ -150,12 +150,55 @@ __device__ __forceinline__ void final_loss_reduce(const float* per_patch, int P,
     if (red) publish_step_stats(*red, static_cast<float>(sum), static_cast<float>(sq), static_cast<float>(P));
 }
 
+// Two-level form for persistent kernels: every CTA leaves {sum, sum_sq, min, max} of ITS patches (fixed patch -> warp
+// -> CTA mapping and summation order, so the result is deterministic for a given grid), the last CTA reduces the
+// gridDim.x partials instead of re-reading all P per-patch values through L2.
+struct LossPartial {
+    double sum, sq;
+    float mn, mx;
+    float pad[2];
+};
+static_assert(sizeof(LossPartial) == 32, "partial layout");
+
+__device__ __forceinline__ void final_partials_reduce(const LossPartial* parts, int nparts, int P, float* total, float* stats,
+                                                      const gm3d_step_reduce_t* red = nullptr) {
+    __shared__ double s_sum[32], s_sq[32];
+    __shared__ float s_mn[32], s_mx[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    double sum = 0.0, sq = 0.0;
+    float mn = FLT_MAX, mx = -FLT_MAX;
+    for (int i = tid; i < nparts; i += blockDim.x) {
+        const double2 a = __ldcg(reinterpret_cast<const double2*>(parts + i));
+        const float2 b = __ldcg(reinterpret_cast<const float2*>(&parts[i].mn));
+        sum += a.x, sq += a.y, mn = fminf(mn, b.x), mx = fmaxf(mx, b.y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(kFull, sum, o);
+        sq += __shfl_xor_sync(kFull, sq, o);
+        mn = fminf(mn, __shfl_xor_sync(kFull, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+    }
+    if (lane == 0) s_sum[warp] = sum, s_sq[warp] = sq, s_mn[warp] = mn, s_mx[warp] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < nw; ++w) sum += s_sum[w], sq += s_sq[w], mn = fminf(mn, s_mn[w]), mx = fmaxf(mx, s_mx[w]);
+        const float mean = static_cast<float>(sum / static_cast<double>(P));
+        if (total) total[0] = mean;
+        if (stats) {
+            stats[0] = static_cast<float>(sum), stats[1] = static_cast<float>(sq), stats[2] = static_cast<float>(P);
+            stats[3] = mn, stats[4] = mx, stats[5] = mean, stats[6] = stats[7] = 0.0f;
+        }
+    }
+    if (red) publish_step_stats(*red, static_cast<float>(sum), static_cast<float>(sq), static_cast<float>(P));
+}
+
 // Returns true in every thread of the CTA that arrives last at `ticket` (and resets the ticket).
 __device__ __forceinline__ bool last_cta(unsigned* ticket) {
     __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
+    __syncthreads();  // every thread's per-patch stores precede thread 0's fence (fences are cumulative)
     if (threadIdx.x == 0) {
+        __threadfence();
         const unsigned t = atomicAdd(ticket, 1u);
         s_last = (t == gridDim.x - 1);
         if (s_last) *ticket = 0u;  // self-resetting: the workspace stays zeroed for the next launch

@@ -41,7 +41,7 @@ def test_version_errors_and_workspace_are_host_only():
     assert lib.gm3d_strerror(0) == b"success"
     assert lib.gm3d_workspace_bytes(_lib.OP_FPS, 4, 1024, 64, 0) == 0          # register-resident kernel
     assert lib.gm3d_workspace_bytes(_lib.OP_FPS, 4, 10000, 64, 0) == 4 * 10000 * 4  # running-min array
-    assert lib.gm3d_workspace_bytes(_lib.OP_CHAMFER_FWD, 4992, 32, 32, 0) == 16 + 4992 * 4
+    assert lib.gm3d_workspace_bytes(_lib.OP_CHAMFER_FWD, 4992, 32, 32, 0) == 16 + 4096 * 32 + 4992 * 4  # ticket, CTA partials, per-patch scratch
     assert lib.gm3d_workspace_bytes(_lib.OP_KNN, 4, 1024, 64, 32) == 0
 
 
