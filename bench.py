@@ -320,7 +320,7 @@ def run_native(args, cfg):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    wd = _watchdog(float(os.environ.get("GM3D_BENCH_WATCHDOG_S", "540")))
+    wd = _watchdog(float(os.environ.get("GM3D_BENCH_WATCHDOG_S", "300")))
     if world > 1:
         # a mismatched / missing collective aborts within the timeout instead of spinning in NCCL kernels
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "1")
@@ -436,8 +436,14 @@ def run_native(args, cfg):
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(R)]
     _stage(f"timed region: {R} repetitions of {K} steps")
     barrier()
+    # Ranks that exchange nothing inside a repetition (collective none / peer: the sums of one replay are formed beside
+    # the next) need no per-repetition alignment -- a repetition's duration on a rank does not depend on when the others
+    # start, and the lagging collect keeps the ranks within one replay of each other.  Coupled modes re-align every time.
+    coupled = mode in ("peer_sync", "peer_step", "nccl")
+    device_align()
     for r in range(R):
-        device_align()
+        if coupled:
+            device_align()
         ev0[r].record()
         run_steps(K)
         ev1[r].record()
@@ -781,7 +787,7 @@ def run_c3(args, cfg):
         raise SystemExit("bench.py: no CUDA device; the gm3d_b200 path has no CPU fallback")
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         raise SystemExit("bench.py --config c3 is a one-GPU configuration")
-    wd = _watchdog(float(os.environ.get("GM3D_BENCH_WATCHDOG_S", "540")))
+    wd = _watchdog(float(os.environ.get("GM3D_BENCH_WATCHDOG_S", "300")))
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     B, N, Gs, ks, ratio, desc = cfg

@@ -75,3 +75,27 @@ def mask_center_rand(center: torch.Tensor, mask_ratio: float, noaug: bool = Fals
     m = ops.hard_mask(None, B, G, G - num_mask, 0, rand_keys=rand_keys, seed=seed, offset=offset,
                       device=center.device)
     return m.view(torch.bool)
+
+
+@torch.no_grad()
+def mask_center_block(center: torch.Tensor, mask_ratio: float, noaug: bool = False,
+                      index: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Drop-in for Point_MAE's `_mask_center_block` (/root/reference/Point-MAE_SA3D/models/Point_MAE.py:268-295):
+    per cloud one random centre and the int(mask_ratio * G) centres nearest to it (itself included) are masked.
+    center (B, G, 3) -> bool mask (B, G).  `index` (B,) chooses the seed centres; None draws them with Python's
+    `random.randint(0, G - 1)` per cloud in batch order -- the reference's own RNG stream.  The selection is the
+    hard-mask kernel on -|c - c_seed|^2 (the reference's argsort of the norm is not a stable sort either, so exact
+    distance ties are unordered in both)."""
+    import random
+    B, G, _ = center.shape
+    if noaug or mask_ratio == 0:
+        return torch.zeros(center.shape[:2], dtype=torch.bool, device=center.device)
+    num_mask = int(mask_ratio * G)
+    if index is None:
+        index = torch.tensor([random.randint(0, G - 1) for _ in range(B)], dtype=torch.long)
+    index = index.to(device=center.device, dtype=torch.long)
+    c = center.float()
+    seed = c.gather(1, index.view(B, 1, 1).expand(B, 1, 3))
+    key = -((c - seed) ** 2).sum(-1)  # largest key = nearest centre
+    m = ops.hard_mask(key.contiguous(), B, G, G - num_mask, num_mask, device=center.device)
+    return m.view(torch.bool)

@@ -482,6 +482,27 @@ def test_generate_mask_dropin(cuda):
     assert not masking.mask_center_rand(torch.zeros(8, 64, 3, device=cuda), 0.6, noaug=True).any()
 
 
+def test_mask_center_block_dropin(cuda):
+    """_mask_center_block (models/Point_MAE.py:268-295): the int(ratio * G) centres nearest to one random centre per
+    cloud, with the reference's own `random.randint` stream, against a NumPy restatement of the reference lines."""
+    import random
+    from gm3d_b200 import masking
+    B, G, ratio = 9, 64, 0.6
+    c = synthetic_clouds(B, G, 123)
+    random.seed(7)
+    got = host(masking.mask_center_block(dev(c, cuda), ratio))
+    random.seed(7)
+    for b in range(B):
+        index = random.randint(0, G - 1)
+        d = np.linalg.norm(c[b, index].reshape(1, 3) - c[b], axis=-1)
+        want = np.zeros(G, dtype=bool)
+        want[np.argsort(d, kind="stable")[: int(ratio * G)]] = True
+        assert np.array_equal(got[b], want) and got[b, index]
+    assert not masking.mask_center_block(dev(c, cuda), ratio, noaug=True).any()
+    idx = torch.arange(B) % G
+    assert host(masking.mask_center_block(dev(c, cuda), 0.25, index=idx)).sum(1).tolist() == [16] * B
+
+
 def test_hard_mask_ties_and_sizes(cuda):
     from gm3d_b200 import ops
     rng = np.random.default_rng(5)
