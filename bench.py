@@ -717,7 +717,8 @@ def run_native(args, cfg):
                     "traffic": nk.get("dram_bytes"), "peak_source": peak_src if not by_fp32 else "148 SM x 128 lanes x 2 x max SM clock (non-tensor FP32)",
                     "hbm_gbs": hbm_gbs, "hbm_peak": hbm_peak, "hbm_frac": hbm_frac,
                     "fp32_tflops": fp32_tf, "fp32_peak": fp32_peak, "fp32_frac": fp32_frac,
-                    "issue_slot_frac": nk.get("issue_slot_frac"), "us_per_launch": dom_us,
+                    "issue_slot_frac": nk.get("issue_slot_frac"),  # of the kernel profiled alone (ncu serialises launches)
+                    "us_per_launch": dom_us,
                     "algorithmic_bytes_per_launch": bpc[dom] * B, "algorithmic_flop_per_launch": 8 * evals.get(dom, 0) * B,
                     "limiter": "instruction issue + the dependent latency of the G-round sampling chain (one CTA per cloud); "
                                "neither roof binds -- see DESIGN.md 4.1"}
@@ -743,10 +744,11 @@ def run_native(args, cfg):
                 "rank_median_ms_per_step": rank_medians,
                 "reps": R, "ms_per_step_min": float(tl[0]) / K, "ms_per_step_p90": float(tl[int(0.9 * (R - 1))]) / K,
                 "timing": f"median over {R} repetitions of the {K}-step region (CUDA events per repetition, max over ranks per "
-                          "repetition; ranks aligned on the device before each repetition)",
+                          "repetition; barrier + device-side alignment before the first repetition" +
+                          (", re-aligned before every repetition" if coupled else "") + ")",
                 "run": {"path": steps[0].path, "kernels_per_step": steps[0].kernels_per_step, "cuda_graph": True,
-                        "step_overlap": ((f"group launches chained by programmatic dependent launch, mask / loss launches on "
-                                          f"forked streams, graphs of up to {ring} steps" if steps[0].group_per_cloud else
+                        "step_overlap": ((f"independent steps (mask -> group -> loss launches each) round-robin on forked streams "
+                                          f"inside graphs of up to {ring} steps" if steps[0].group_per_cloud else
                                           f"independent steps round-robin on {os.environ.get('GM3D_RING_LANES', '4')} forked streams "
                                           f"inside graphs of up to {ring} steps") if overlap else "none"),
                         "collective": collective},

@@ -215,7 +215,9 @@ __global__ void __launch_bounds__(CW * 32, 32 / CW)
     pdl_enter(flags);
     double acc_sum = 0.0, acc_sq = 0.0;  // this warp's patches, in trip order (identical in every lane)
     float acc_mn = FLT_MAX, acc_mx = -FLT_MAX;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the warp index through a broadcast: the compiler then knows that the trip loop is warp-uniform and emits the
+    // collectives inside it (REDUX, VOTE, MATCH, SHFL) without a WARPSYNC / ENDCOLLECTIVE pair around each
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(kFull, static_cast<int>(threadIdx.x >> 5), 0);
     ChamferWarpScratch* sc = &s_sc[warp];
     const int warps_total = gridDim.x * CW;
     const int nf = 3 * k;

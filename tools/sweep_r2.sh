@@ -1,5 +1,2 @@
-python tools/quick_step.py --path dataflow --check
-python tools/quick_step.py --path single --check
-python tools/quick_step.py --path dataflow --parts c
-python tools/bench_c5_chamfer.py
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+export GM3D_KNN_XSORT_MIN=1024
+for m in 0 1 2; do echo "mode $m"; GM3D_XS_MODE=$m python tools/bench_knn.py 2>&1 | head -1; done
