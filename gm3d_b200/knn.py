@@ -15,7 +15,8 @@ class KNN(nn.Module):
     transpose_mode=True : ref (B, N, dim), query (B, G, dim) -> D, I of shape (B, G, k)
     transpose_mode=False: ref (B, dim, N), query (B, dim, G) -> D, I of shape (B, k, G)
     D is float32 (sqrt applied), I is int64, 0-based.  Runs under no_grad like the original.
-    The whole batch is one kernel launch (the original loops over the batch in Python).
+    The whole batch is one kernel launch (the original loops over the batch in Python).  dim == 3 and k <= 32 (every
+    reference configuration) run the specialised kernels, anything else the general selection kernel.
     """
 
     def __init__(self, k: int, transpose_mode: bool = False):

@@ -106,11 +106,11 @@ def knn(ref: torch.Tensor, query: torch.Tensor, k: int, want_dist: bool = True):
     """ref (B,N,3), query (B,G,3) f32 -> D (B,G,k) f32 euclidean (or None), I (B,G,k) int64."""
     _req(ref, "ref", torch.float32, 3)
     _req(query, "query", torch.float32, 3)
-    if ref.shape[2] != 3 or query.shape[2] != 3:
-        raise NotImplementedError("gm3d_b200 kNN is specialised to 3-D points (dim == 3)")
+    if ref.shape[2] != query.shape[2]:
+        raise ValueError("ref and query disagree on the point dimension")
     if ref.shape[0] != query.shape[0]:
         raise ValueError("ref and query disagree on the batch size")
-    B, N, _ = ref.shape
+    B, N, dim = ref.shape
     G = query.shape[1]
     k = int(k)
     if k > N or k <= 0:
@@ -120,8 +120,12 @@ def knn(ref: torch.Tensor, query: torch.Tensor, k: int, want_dist: bool = True):
         D = torch.empty((B, G, k), dtype=torch.float32, device=ref.device) if want_dist else None
         if I.numel() == 0:
             return D, I
-        rc = _lib.load().gm3d_knn_f32(_p(ref), _p(query), B, N, G, k, _p(D), _p(I), None, _stream(ref))
-    _lib.check("gm3d_knn_f32", rc)
+        if dim == 3 and k <= _lib.KNN_MAX_K:  # every reference configuration: the specialised kernels
+            rc = _lib.load().gm3d_knn_f32(_p(ref), _p(query), B, N, G, k, _p(D), _p(I), None, _stream(ref))
+            _lib.check("gm3d_knn_f32", rc)
+        else:  # no shape limits, like upstream: the general selection kernel
+            rc = _lib.load().gm3d_knn_general_f32(_p(ref), _p(query), B, N, G, dim, k, _p(D), _p(I), _stream(ref))
+            _lib.check("gm3d_knn_general_f32", rc)
     return D, I
 
 

@@ -15,9 +15,9 @@ interleave with its networks ("dataflow" path, the default and what bench.py tim
 
 The "single" path issues the same work as ONE launch (gm3d_cloud_step_f32 with `pred`); it serves callers whose
 prediction does not depend on this step's grouping / mask and is reported by bench.py as `single_launch`.
-`StepRing` replays a ring of independent steps as one graph: the group launches chain by programmatic dependent
-launch on one stream, masks and Chamfer launches run on two forked streams behind their own step's group launch,
-so the loss of step i overlaps the sampling of step i+1.  `HostStagedStep` adds the host<->device copies from/to
+`StepRing` replays a ring of independent steps as one graph: every step is the stream-ordered sequence mask -> group ->
+loss, the steps go round-robin to forked streams, so the latency-bound loss launch of one step runs beside the sampling
+chains of the others.  GM3D_NVTX=1 wraps the enqueue stages in NVTX ranges.  `HostStagedStep` adds the host<->device copies from/to
 pinned memory (the end-to-end arm of bench.py).
 """
 from __future__ import annotations
@@ -32,6 +32,23 @@ from . import _lib
 from .masking import mask_lengths
 
 FUSED_LANES_MAX_B = int(os.environ.get("GM3D_FUSED_LANES_MAX_B", "148"))  # tuning aid
+_NVTX = os.environ.get("GM3D_NVTX", "0") == "1"  # NVTX ranges around the enqueue stages (nsys / ncu --nvtx timelines)
+
+
+class _nvtx:
+    """`with _nvtx("gm3d.group"):` -- a named NVTX range when GM3D_NVTX=1, nothing otherwise."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
 FUSED_MAX_N, FUSED_MAX_G = 2048, 1024  # gm3d_cloud_step_f32 serves these; larger clouds use fps + knn_group
 
 
@@ -146,21 +163,23 @@ class GroupLossStep:
         L, p = self.lib, (lambda t: None if t is None else t.data_ptr())
         st = torch.cuda.current_stream(self.dev).cuda_stream
         B, N, G, k = self.B, self.N, self.G, self.k
-        if self.group_per_cloud:  # Group.forward by the per-cloud kernel; `flags` chain independent steps
-            _lib.check("gm3d_cloud_step_f32", L.gm3d_cloud_step_f32(
-                p(self.xyz), B, N, G, k, p(self.fps_idx), p(self.center), None, p(self.neighborhood), None,
-                None, 0, 0, None, 0, 0, None, None, None, 0.0, 0.0, 2, None, None, None, None, None, None, None, None,
-                flags, None, None, st))
-        else:
-            _lib.check("gm3d_group_f32", L.gm3d_group_f32(p(self.xyz), B, N, G, k, p(self.fps_idx), p(self.center), None,
-                                                          p(self.neighborhood), None, p(self.ws), st))
+        with _nvtx("gm3d.group"):
+            if self.group_per_cloud:  # Group.forward by the per-cloud kernel; `flags` chain independent steps
+                _lib.check("gm3d_cloud_step_f32", L.gm3d_cloud_step_f32(
+                    p(self.xyz), B, N, G, k, p(self.fps_idx), p(self.center), None, p(self.neighborhood), None,
+                    None, 0, 0, None, 0, 0, None, None, None, 0.0, 0.0, 2, None, None, None, None, None, None, None, None,
+                    flags, None, None, st))
+            else:
+                _lib.check("gm3d_group_f32", L.gm3d_group_f32(p(self.xyz), B, N, G, k, p(self.fps_idx), p(self.center), None,
+                                                              p(self.neighborhood), None, p(self.ws), st))
 
     def enqueue_mask(self, flags: int = 0) -> None:
         p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         st = torch.cuda.current_stream(self.dev).cuda_stream
-        _lib.check("gm3d_hard_mask_f32", self.lib.gm3d_hard_mask_f32(
-            p(self.loss_pred), self.B, self.G, self.len_keep, self.len_loss, None, self.seed, self.rand_offset,
-            p(self.mask), p(self.patch_index), flags, st))
+        with _nvtx("gm3d.mask"):
+            _lib.check("gm3d_hard_mask_f32", self.lib.gm3d_hard_mask_f32(
+                p(self.loss_pred), self.B, self.G, self.len_keep, self.len_loss, None, self.seed, self.rand_offset,
+                p(self.mask), p(self.patch_index), flags, st))
 
     def _gscale(self) -> float:
         return (1.0 if self.norm == 2 else 0.5) / (self.P * self.k)  # d mean / d dist (L1: the outer /2 folded in)
@@ -169,10 +188,11 @@ class GroupLossStep:
         p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         st = torch.cuda.current_stream(self.dev).cuda_stream
         g, k = self._gscale(), self.k
-        _lib.check("gm3d_chamfer_fused_f32", self.lib.gm3d_chamfer_fused_f32(
-            p(self.pred), p(self.neighborhood), p(self.patch_index), self.P, k, k, g, g, p(self.dist1), p(self.dist2),
-            p(self.idx1), p(self.idx2), p(self.per_patch), p(self.total), p(self.stats), self.norm, p(self.grad_pred),
-            None, ctypes.byref(reduce) if reduce is not None else None, flags, p(self.cd_ws), st))
+        with _nvtx("gm3d.loss"):
+            _lib.check("gm3d_chamfer_fused_f32", self.lib.gm3d_chamfer_fused_f32(
+                p(self.pred), p(self.neighborhood), p(self.patch_index), self.P, k, k, g, g, p(self.dist1), p(self.dist2),
+                p(self.idx1), p(self.idx2), p(self.per_patch), p(self.total), p(self.stats), self.norm, p(self.grad_pred),
+                None, ctypes.byref(reduce) if reduce is not None else None, flags, p(self.cd_ws), st))
 
     def enqueue(self, flags: int = 0, reduce: Optional[_lib.StepReduce] = None) -> None:
         """Enqueue the kernels of one step on torch's current stream (+ one forked side stream for the mask).
@@ -476,10 +496,11 @@ class StepRing:
         return self
 
     def run(self) -> None:
-        if self.graph is not None:
-            self.graph.replay()
-        else:
-            self.enqueue()
+        with _nvtx(f"gm3d.ring[{len(self.steps)}]"):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self.enqueue()
 
 
 class HostStagedStep(GroupLossStep):

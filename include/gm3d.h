@@ -12,6 +12,7 @@
  *   gm3d_gather_f32         pointnet2_utils.gather_operation        utils/miscc.py:19, engine_finetune.py:134
  *   gm3d_gather_grad_f32    GatherOperation.backward                (autograd of the above)
  *   gm3d_knn_f32            knn_cuda.KNN(k, transpose_mode).forward models/Point_MAE.py:55,68
+ *   gm3d_knn_general_f32    the same for k > 32 or dim != 3        (no call site in the reference uses it)
  *   gm3d_knn_group_f32      Group.forward lines 68-77 (knn -> gather -> centre)    models/Point_MAE.py:68-77
  *   gm3d_group_f32          Group.forward (fps -> knn -> gather -> centre)   models/Point_MAE.py:57-78,
  *                                                                   ..._feature_besed.py:1238-1260
@@ -177,6 +178,13 @@ int gm3d_gather_grad_f32(const float* gout, const int32_t* idx, int B, int C, in
  * (distance, ref index); dist (B,G,k) f32 EUCLIDEAN (sqrt) or NULL.  1 <= k <= min(N, GM3D_KNN_MAX_K). */
 int gm3d_knn_f32(const float* ref, const float* query, int B, int N, int G, int k, float* dist /* or NULL */,
                  int64_t* idx, void* ws, void* stream);
+
+/* The same operator without shape limits: any point dimension `dim` >= 1 (ref (B,N,dim), query (B,G,dim)), any
+ * 1 <= k <= N; N <= 51200 (the distances of one query live in shared memory).  KNN_CUDA's expression (`ssd += t*t` per
+ * dimension, FMA-contracted) and order (ascending by (distance, index)).  A plain selection kernel -- use gm3d_knn_f32
+ * for 3-D points and k <= 32, which every reference configuration does. */
+int gm3d_knn_general_f32(const float* ref, const float* query, int B, int N, int G, int dim, int k,
+                         float* dist /* or NULL */, int64_t* idx, void* stream);
 
 /* kNN patches around GIVEN centres + gather + centre-normalisation (the second half of Group.forward,
  * models/Point_MAE.py:68-77).  xyz (B,N,3), centers (B,G,3) -> knn_idx (B,G,k) int64 or NULL,

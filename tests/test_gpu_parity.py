@@ -152,8 +152,35 @@ def test_knn_all_ties_and_transpose_mode(cuda):
     assert np.array_equal(host(I0), Iw.transpose(0, 2, 1)) and np.array_equal(host(D0), Dw.transpose(0, 2, 1))
     with pytest.raises(ValueError):
         KNN(301, True)(dev(xyz, cuda), dev(qq, cuda))
-    with pytest.raises(NotImplementedError):
-        KNN(33, True)(dev(xyz, cuda), dev(qq, cuda))
+
+
+@pytest.mark.parametrize("B,N,G,dim,k", [(2, 300, 11, 3, 33), (2, 1024, 20, 3, 64), (1, 5000, 7, 3, 100), (2, 200, 9, 2, 5),
+                                         (2, 257, 13, 5, 40), (1, 64, 64, 16, 64), (1, 3, 2, 1, 3)])
+def test_knn_general_any_k_any_dim(cuda, B, N, G, dim, k):
+    """k > 32 or dim != 3 (upstream KNN_CUDA has no such limits): the general selection kernel, bit-exact against the
+    C oracle for dim == 3 and against a NumPy restatement of `ssd += t*t` per dimension (exact FMA) otherwise;
+    duplicate points included (ties -> lower index)."""
+    from gm3d_b200.knn import KNN
+    rng = np.random.default_rng(N + dim + k)
+    ref = rng.standard_normal((B, N, dim)).astype(np.float32)
+    ref[:, N // 2:N // 2 + N // 8] = ref[:, :N // 8]  # duplicates
+    q = np.stack([ref[b, rng.choice(N, G, replace=G > N)] for b in range(B)])
+    q[:, ::2] += (rng.standard_normal((B, q[:, ::2].shape[1], dim)) * 0.1).astype(np.float32)
+    D, I = KNN(k, transpose_mode=True)(dev(ref, cuda), dev(q, cuda))
+    if dim == 3:
+        Dw, Iw = co.knn(ref, q, k)
+    else:
+        d = np.zeros((B, G, N), dtype=np.float32)
+        for c in range(dim):
+            t = (ref[:, None, :, c] - q[:, :, None, c]).astype(np.float32)
+            d = co.fmaf(t, t, d).reshape(B, G, N)
+        Iw = np.argsort(d, axis=2, kind="stable")[:, :, :k]
+        Dw = np.sqrt(np.take_along_axis(d, Iw, axis=2))
+    assert I.dtype == torch.int64 and tuple(I.shape) == (B, G, k)
+    assert np.array_equal(host(I), Iw)
+    assert np.array_equal(host(D).view(np.uint32), Dw.view(np.uint32))
+    Dt, It = KNN(k, transpose_mode=False)(dev(ref.transpose(0, 2, 1), cuda), dev(q.transpose(0, 2, 1), cuda))
+    assert np.array_equal(host(It), Iw.transpose(0, 2, 1)) and tuple(Dt.shape) == (B, k, G)
 
 
 @pytest.mark.parametrize("B,N,G,k", [
@@ -789,14 +816,18 @@ def test_step_ring_dataflow_equals_serial_steps(cuda):
         for n in want[-1]:
             getattr(s, n).fill_(0)
         steps.append(s)
-    ring = StepRing(steps).capture()
-    for _ in range(3):
-        ring.run()
-    torch.cuda.synchronize()
-    for i, (s, w) in enumerate(zip(steps, want)):
-        for n, v in w.items():
-            assert np.array_equal(host(getattr(s, n)), v), (i, n)
-        assert np.array_equal(host(ring.head[i, :3]), host(s.stats[:3])) and ring.head[i, 3].item() == 1.0
+    for schedule in ("lanes", "chain"):  # forked streams (default) / one programmatic-dependent-launch chain G0 M0 G1 C0 M1 ...
+        for s, w in zip(steps, want):
+            for n in w:
+                getattr(s, n).fill_(0)
+        ring = StepRing(steps, schedule=schedule).capture()
+        for _ in range(3):
+            ring.run()
+        torch.cuda.synchronize()
+        for i, (s, w) in enumerate(zip(steps, want)):
+            for n, v in w.items():
+                assert np.array_equal(host(getattr(s, n)), v), (schedule, i, n)
+            assert np.array_equal(host(ring.head[i, :3]), host(s.stats[:3])) and ring.head[i, 3].item() == 1.0
 
 
 @pytest.mark.parametrize("path", ["dataflow", "single"])
