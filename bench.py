@@ -52,10 +52,34 @@ def synthetic_batch(B, N, G, k, M, seed):
     x /= np.linalg.norm(x, axis=-1).max(axis=1)[:, None, None]
     x = x * rng.uniform(2 / 3, 3 / 2, (B, 1, 3)) + rng.uniform(-0.2, 0.2, (B, 1, 3))
     loss_pred = rng.standard_normal((B, G))
-    # predicted patches: centre-normalised neighbourhood-sized blobs (radius ~ patch radius) -- the decoder's
-    # output distribution; values do not change the work done.
+    # placeholder predictions (patch-sized blobs); the timed inputs replace them by near_target_pred() / the CPU twin
+    # below -- SURVEY 8(d): pred = gt + 0.02 * randn, which needs the grouping and the mask first
     pred = rng.standard_normal((B * M, k, 3)) * 0.08
     return x.astype(np.float32), loss_pred.astype(np.float32), pred.astype(np.float32)
+
+
+def near_target_pred(s, seed):
+    """the prediction is the masked target patch plus 0.02 * N(0, 1) noise (a decoder output near its
+    target: every target point's nearest prediction is then usually its own, as in training, instead of the
+    many-to-one matches random blobs produce).  Set-up only: runs the step's mask and group launches, then fills
+    `s.pred` on the device; returns the prediction as a NumPy array."""
+    import torch
+    s.enqueue_mask()
+    s.enqueue_group()
+    torch.cuda.synchronize(s.dev)
+    g = torch.Generator(device=s.dev)
+    g.manual_seed(seed)
+    gt = s.neighborhood.view(s.B * s.G, s.k, 3)[s.patch_index.long()]
+    s.pred.copy_(gt + 0.02 * torch.randn(gt.shape, generator=g, device=s.dev, dtype=torch.float32))
+    return s.pred.cpu().numpy()
+
+
+def near_target_pred_cpu(co, x, lp, G, k, len_keep, len_loss, rk, seed):
+    """The CPU arm's twin of near_target_pred (same law; the oracle's own grouping and mask)."""
+    nb = co.group(x, G, k)["neighborhood"]
+    mask = co.hard_mask(lp, len_keep, len_loss, rk).astype(bool)
+    gt = nb[mask]
+    return (gt + 0.02 * np.random.default_rng(seed).standard_normal(gt.shape)).astype(np.float32)
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -176,9 +200,13 @@ def cpu_step_m2ae(co, cfg, x, lps, preds, rks):
 def time_cpu_m2ae(cfg, budget_s: float, steps=None, warmup: int = 1):
     from oracle import c_oracle as co
     B = cfg[0]
-    x, lps, preds = m2ae_inputs(cfg, 1234)
+    x, lps, _ = m2ae_inputs(cfg, 1234)
     lv = m2ae_levels(cfg)
     rks = [np.random.default_rng(5 + i).random((B, l[1])).astype(np.float32) for i, l in enumerate(lv)]
+    preds, cloud = [], x
+    for i, ((n, g, k, m, len_keep, len_loss), lp, rk) in enumerate(zip(lv, lps, rks)):
+        preds.append(near_target_pred_cpu(co, cloud, lp, g, k, len_keep, len_loss, rk, 1235 + i))
+        cloud = co.group(cloud, g, k)["center"]
     sample_B = max(co.num_threads(), min(B, 16))
     sub = lambda b: (x[:b], [a[:b] for a in lps], [p[: b * l[3]] for p, l in zip(preds, lv)], [r[:b] for r in rks])  # noqa: E731
     t0 = time.perf_counter()
@@ -209,8 +237,9 @@ def time_cpu(cfg, budget_s: float, steps=None, warmup: int = 1):
     B, N, G, k, ratio, _ = cfg
     len_keep, len_loss = mask_lengths(G, ratio, 199, 400)
     M = G - len_keep
-    x, lp, pred = synthetic_batch(B, N, G, k, M, 1234)
+    x, lp, _ = synthetic_batch(B, N, G, k, M, 1234)
     rk = np.random.default_rng(5).random((B, G)).astype(np.float32)
+    pred = near_target_pred_cpu(co, x, lp, G, k, len_keep, len_loss, rk, 1235)
     t0 = time.perf_counter()
     cpu_step(co, x, lp, pred, G, k, len_keep, len_loss, rk)  # warm-up + calibration
     one = time.perf_counter() - t0
@@ -360,8 +389,9 @@ def run_native(args, cfg):
     steps, inputs = [], []
     for r in range(ring):
         s = GroupLossStep(B, N, G, k, ratio, device=dev, seed=1234, rand_offset=(rank * ring + r) * B * G)
-        x, lp, pred = synthetic_batch(B, N, G, k, M, 1234 + 1000 * rank + r)
-        s.xyz.copy_(torch.from_numpy(x)); s.loss_pred.copy_(torch.from_numpy(lp)); s.pred.copy_(torch.from_numpy(pred))
+        x, lp, _ = synthetic_batch(B, N, G, k, M, 1234 + 1000 * rank + r)
+        s.xyz.copy_(torch.from_numpy(x)); s.loss_pred.copy_(torch.from_numpy(lp))
+        pred = near_target_pred(s, 99 + 1000 * rank + r)
         steps.append(s)
         inputs.append((x, lp, pred) if r == 0 else None)
 
@@ -623,10 +653,10 @@ def run_native(args, cfg):
             sub = []
             for r in range(SUB):
                 s = HostStagedStep(B, N, G, k, ratio, device=dev, seed=1234, rand_offset=(gi * SUB + r) * B * G, cloud_only=cloud_only)
-                x, lp, pred = synthetic_batch(B, N, G, k, M, 4321 + 1000 * rank + gi * SUB + r)
+                x, lp, _ = synthetic_batch(B, N, G, k, M, 4321 + 1000 * rank + gi * SUB + r)
+                s.xyz.copy_(torch.from_numpy(x)); s.loss_pred.copy_(torch.from_numpy(lp))
+                pred = near_target_pred(s, 4321 + 1000 * rank + gi * SUB + r)  # leaves s.pred / s.loss_pred on the device too
                 s.h_xyz.copy_(torch.from_numpy(x)); s.h_pred.copy_(torch.from_numpy(pred)); s.h_loss_pred.copy_(torch.from_numpy(lp))
-                if cloud_only:
-                    s.pred.copy_(s.h_pred); s.loss_pred.copy_(s.h_loss_pred)
                 sub.append(s)
             out.append(HostStagedGroup(sub).capture())
         torch.cuda.synchronize()
@@ -799,16 +829,17 @@ def run_c3(args, cfg):
     lv = m2ae_levels(cfg)
 
     def fill(s, seed, host=False):
-        x, lps, preds = m2ae_inputs(cfg, seed)
+        x, lps, _ = m2ae_inputs(cfg, seed)
+        s.xyz.copy_(torch.from_numpy(x))
+        preds = []
+        for li, (l, lp) in enumerate(zip(s.levels, lps)):  # level by level: level l+1 groups level l's centres
+            l.loss_pred.copy_(torch.from_numpy(lp))
+            preds.append(near_target_pred(l, seed + 17 * li))
         if host:
             s.h_views[0][0].copy_(torch.from_numpy(x))
             for li in range(len(lv)):
                 v = s.h_views[li]
                 v[-2].copy_(torch.from_numpy(preds[li])); v[-1].copy_(torch.from_numpy(lps[li]))
-        else:
-            s.xyz.copy_(torch.from_numpy(x))
-            for l, lp, pr in zip(s.levels, lps, preds):
-                l.loss_pred.copy_(torch.from_numpy(lp)); l.pred.copy_(torch.from_numpy(pr))
         return x, lps, preds
 
     steps, first = [], None

@@ -842,8 +842,9 @@ def test_step_ring_bench_variant_every_slot_vs_oracle(cuda, path):
     steps, inputs = [], []
     for r in range(ring_n):
         s = GroupLossStep(B, N, G, k, ratio, device=cuda, seed=1234, rand_offset=r * B * G, path=path)
-        x, lp, pred = bench.synthetic_batch(B, N, G, k, s.M, 1234 + r)
-        s.xyz.copy_(dev(x, cuda)); s.loss_pred.copy_(dev(lp, cuda)); s.pred.copy_(dev(pred, cuda))
+        x, lp, _ = bench.synthetic_batch(B, N, G, k, s.M, 1234 + r)
+        s.xyz.copy_(dev(x, cuda)); s.loss_pred.copy_(dev(lp, cuda))
+        pred = bench.near_target_pred(s, 99 + r)  # the bench's predictions: masked target + 0.02 * noise
         steps.append(s)
         inputs.append((x, lp, pred))
     ring = StepRing(steps).capture()

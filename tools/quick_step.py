@@ -25,8 +25,9 @@ ring = bench.ring_size(B, N, G, k, M)
 steps, inp = [], None
 for r in range(ring):
     s = GroupLossStep(B, N, G, k, ratio, device=dev, seed=1234, rand_offset=r * B * G, path=a.path)
-    x, lp, pred = bench.synthetic_batch(B, N, G, k, M, 1234 + r)
-    s.xyz.copy_(torch.from_numpy(x)); s.loss_pred.copy_(torch.from_numpy(lp)); s.pred.copy_(torch.from_numpy(pred))
+    x, lp, _ = bench.synthetic_batch(B, N, G, k, M, 1234 + r)
+    s.xyz.copy_(torch.from_numpy(x)); s.loss_pred.copy_(torch.from_numpy(lp))
+    pred = bench.near_target_pred(s, 99 + r)  # target + 0.02 * noise
     steps.append(s)
     if r == 0:
         inp = (x, lp, pred)
