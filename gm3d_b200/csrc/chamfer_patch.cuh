@@ -77,10 +77,14 @@ __device__ __forceinline__ ChamferWarpOut chamfer_patch_warp(float ax, float ay,
     // it is parked in shared memory by one lane and lane j picks column j up afterwards (no per-column selects).  The
     // minimum itself is re-evaluated by lane j from its arg-min (same expression => same bits).
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const unsigned mn = __reduce_min_sync(kFull, D[j]);
-        const unsigned bal = __ballot_sync(kFull, D[j] == mn);
-        if (lane == 0) sc->col[j] = bal;
+    for (int j = 0; j < 32; j += 4) {  // four columns per 16-byte store
+        unsigned bal[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const unsigned mn = __reduce_min_sync(kFull, D[j + e]);
+            bal[e] = __ballot_sync(kFull, D[j + e] == mn);
+        }
+        if (lane == 0) *reinterpret_cast<uint4*>(&sc->col[j]) = make_uint4(bal[0], bal[1], bal[2], bal[3]);
     }
     __syncwarp();
     const int besti2 = __ffs(sc->col[lane]) - 1;  // lowest lane = upstream's first minimum
