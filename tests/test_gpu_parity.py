@@ -625,6 +625,36 @@ def test_forward_loss_fused_default_agrees_with_the_step(cuda):
     assert (pred2.grad.double() - p64.grad).abs().max() <= RTOL * p64.grad.abs().max()
 
 
+def test_three_launches_with_networks_in_between(cuda):
+    """the step as a training loop issues it -- group launch, [teacher], mask launch,
+    [student], loss launch -- on the caller's stream, inputs arriving between the launches, equals the captured step."""
+    from gm3d_b200.pipeline import GroupLossStep
+    B, N, G, k = 5, 1024, 64, 32
+    rng = np.random.default_rng(61)
+    x = synthetic_clouds(B, N, 91)
+    lp = rng.standard_normal((B, G)).astype(np.float32)
+    a = GroupLossStep(B, N, G, k, 0.6, device=cuda, seed=2, rand_offset=9)
+    b = GroupLossStep(B, N, G, k, 0.6, device=cuda, seed=2, rand_offset=9)
+    pred = (rng.standard_normal((a.P, k, 3)) * 0.08).astype(np.float32)
+    for s in (a, b):
+        s.loss_pred.fill_(0); s.pred.fill_(0)
+    b.xyz.copy_(dev(x, cuda)); b.loss_pred.copy_(dev(lp, cuda)); b.pred.copy_(dev(pred, cuda))
+    b.capture().run()
+    st = torch.cuda.Stream(cuda)
+    with torch.cuda.stream(st):
+        a.xyz.copy_(dev(x, cuda), non_blocking=True)
+        a.enqueue_group()
+        teacher_out = a.neighborhood.sum() * 0 + dev(lp, cuda)      # "teacher": consumes the grouping, emits loss_pred
+        a.loss_pred.copy_(teacher_out)
+        a.enqueue_mask()
+        student_out = dev(pred, cuda) + a.mask.sum() * 0              # "student": consumes grouping + mask, emits pred
+        a.pred.copy_(student_out)
+        a.enqueue_loss()
+    torch.cuda.synchronize()
+    for n in ("fps_idx", "center", "neighborhood", "mask", "patch_index", "dist1", "idx2", "per_patch", "total", "stats", "grad_pred"):
+        assert torch.equal(getattr(a, n), getattr(b, n)), n
+
+
 def test_loss_stats(cuda):
     from gm3d_b200 import ops
     v = torch.rand(4992, device=cuda)
