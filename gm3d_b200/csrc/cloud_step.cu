@@ -420,6 +420,7 @@ static int launch_cloud_step(const CloudStepParams& p, size_t smem, cudaStream_t
         // workers per SM hide each other's latency (measured, C2: 18.9 -> 17.4 us per step; 64 / 72 / 80: 19.2 / 19.1 / 18.9).
 #ifdef GM3D_TUNING_ENV
         const int regs = tuning_env_int("GM3D_CS_REGS", 56);
+        if (regs == 48) return launch_cloud_step_k(cloud_step_kernel_r<FW, PPT, WARPS, LOSS, 48>, WARPS * 32, p, smem, st);
         if (regs == 64) return launch_cloud_step_k(cloud_step_kernel_r<FW, PPT, WARPS, LOSS, 64>, WARPS * 32, p, smem, st);
         if (regs == 72) return launch_cloud_step_k(cloud_step_kernel_r<FW, PPT, WARPS, LOSS, 72>, WARPS * 32, p, smem, st);
         if (regs == 80) return launch_cloud_step_k(cloud_step_kernel<FW, PPT, WARPS, LOSS>, WARPS * 32, p, smem, st);
