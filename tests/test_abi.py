@@ -85,6 +85,27 @@ def test_argument_validation_returns_einval_without_a_device():
         _lib.check("x", 700)  # a cudaError_t
 
 
+def test_step_reduce_struct_matches_the_header(tmp_path):
+    """gm3d_step_reduce_t is passed by HOST pointer from ctypes: every field offset and the size of _lib.StepReduce must
+    equal what a C compiler makes of include/gm3d.h (compiled here with gcc), and the header must be plain C."""
+    from gm3d_b200 import _lib
+    src = tmp_path / "off.c"
+    fields = ["head", "world", "rank", "inbox", "epoch", "timeout_us", "defer", "status", "collected"]
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gm3d.h"\nint main(void) {\n'
+                   + "".join(f'  printf("{f} %zu\\n", offsetof(gm3d_step_reduce_t, {f}));\n' for f in fields)
+                   + '  printf("sizeof %zu\\n", sizeof(gm3d_step_reduce_t));\n'
+                   + '  printf("inbox_bytes %d\\n", GM3D_INBOX_BYTES);\n  printf("abi %d\\n", GM3D_ABI_VERSION);\n  return 0;\n}\n')
+    exe = tmp_path / "off"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    for f in fields:
+        assert int(got[f]) == getattr(_lib.StepReduce, f).offset, f
+    assert int(got["sizeof"]) == ctypes.sizeof(_lib.StepReduce)
+    assert int(got["inbox_bytes"]) == _lib.INBOX_BYTES and int(got["abi"]) == _lib.GM3D_ABI_VERSION
+
+
 def test_missing_library_fails_loudly(tmp_path):
     """No silent fallback: with the .so absent the operators cannot even be loaded."""
     code = (
