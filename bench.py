@@ -213,7 +213,7 @@ def time_cpu_m2ae(cfg, budget_s: float, steps=None, warmup: int = 1):
     cpu_step_m2ae(co, cfg, *sub(sample_B))
     one = time.perf_counter() - t0
     if steps is None:
-        steps = max(2, min(50, int(budget_s / max(one, 1e-4))))
+        steps = max(2, min(500, int(budget_s / max(one, 1e-4))))
     elif one * (steps + warmup) > budget_s:
         sample_B = max(co.num_threads(), int(sample_B * budget_s / (one * (steps + warmup))))
     args = sub(sample_B)
@@ -245,7 +245,7 @@ def time_cpu(cfg, budget_s: float, steps=None, warmup: int = 1):
     one = time.perf_counter() - t0
     sample_B = B
     if steps is None:
-        steps = max(3, min(200, int(budget_s / max(one, 1e-4))))
+        steps = max(3, min(2000, int(budget_s / max(one, 1e-4))))  # ~budget_s seconds of CPU work
     elif one * (steps + warmup) > budget_s:  # shrink the per-step sample, keep whole clouds
         sample_B = max(co.num_threads(), int(B * budget_s / (one * (steps + warmup))))
         sample_B = min(B, sample_B)

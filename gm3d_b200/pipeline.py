@@ -597,5 +597,6 @@ class HostStagedGroup:
             self.done.record()
 
     def losses(self):
+        """The steps' mean per-patch losses (statistics slot 5), read from pinned memory after the group's D2H copies."""
         self.done.synchronize()
-        return [float(v[0]) for v in self.h_stats_np]
+        return [float(v[5]) for v in self.h_stats_np]
