@@ -317,3 +317,18 @@ def encoder_eval(point_groups, sd, eps=1e-5):
     h2 = np.maximum(bn(conv(cat, sd["second_conv.0.weight"], sd["second_conv.0.bias"]), "second_conv.1"), 0.0)
     out = conv(h2, sd["second_conv.3.weight"], sd["second_conv.3.bias"]).max(axis=1)
     return out.reshape(bs, g, -1)
+
+
+# ---------------------------------------------------------------------------------------------
+# a9' _mask_center_block (models/Point_MAE.py:268-295): per cloud the int(ratio * G) centres nearest to one picked
+# centre (torch.norm of the difference, argsort ascending) are masked
+# ---------------------------------------------------------------------------------------------
+def mask_center_block(center, mask_ratio: float, picks):
+    center = np.asarray(center, dtype=F32)
+    B, G, _ = center.shape
+    num = int(mask_ratio * G)
+    out = np.zeros((B, G), dtype=bool)
+    for b in range(B):
+        d = np.sqrt(((center[b, picks[b]][None] - center[b]) ** 2).sum(-1, dtype=F32))
+        out[b, np.argsort(d, kind="stable")[:num]] = True
+    return out

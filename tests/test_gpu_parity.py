@@ -526,6 +526,13 @@ def test_mask_center_block_dropin(cuda):
         want[np.argsort(d, kind="stable")[: int(ratio * G)]] = True
         assert np.array_equal(got[b], want) and got[b, index]
     assert not masking.mask_center_block(dev(c, cuda), ratio, noaug=True).any()
+    # against the reference method's own output (tests/golden/reference_block_mask.npz), same `random` stream
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_block_mask.npz"))
+    for tag in g["cases"]:
+        random.seed(int(g[f"{tag}_seed"][0]))
+        got = host(masking.mask_center_block(dev(g[f"{tag}_centers"], cuda), float(g[f"{tag}_ratio"][0])))
+        assert np.array_equal(got, g[f"{tag}_mask"]), tag
     idx = torch.arange(B) % G
     assert host(masking.mask_center_block(dev(c, cuda), 0.25, index=idx)).sum(1).tolist() == [16] * B
 

@@ -91,3 +91,37 @@ def test_bench_configs_match_baseline_json():
     x, lp, pred = bench.synthetic_batch(4, 256, 16, 8, 9, 0)
     assert x.shape == (4, 256, 3) and x.dtype == np.float32 and lp.shape == (4, 16) and pred.shape == (36, 8, 3)
     assert np.abs(x).max() < 2.0
+
+
+def test_bench_config_dict_is_shared_by_both_arms_and_c3_is_the_m2ae_hierarchy():
+    """Both arms print bench.config_dict (same keys and values => the driver's same_config), the ring is larger than
+    L2, and --config c3 is BASELINE config[2]: groups 512/256/64, sizes 16/8/8, level l+1 on level l's centres."""
+    import json
+    import os
+    import bench
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    base = json.load(open(os.path.join(root, "BASELINE.json")))
+    c2 = bench.config_dict(bench.CONFIGS["c2"])
+    assert c2["M"] == 39 and set(c2) == {"workload", "B_per_gpu", "N", "G", "k", "M", "l2_policy"}
+    B, N, G, k, M = 128, 1024, 64, 32, 39
+    assert bench.ring_size(B, N, G, k, M) * bench.buffer_set_bytes(B, N, G, k, M) >= 2 * bench.L2_BYTES
+    assert 11e6 < bench.buffer_set_bytes(B, N, G, k, M) < 12e6  # "x 11.3 MB" in l2_policy
+    c3 = bench.config_dict(bench.CONFIGS["c3"])
+    assert c3["G"] == [512, 256, 64] and c3["k"] == [16, 8, 8] and c3["N"] == 2048 and "512/256/64" in base["configs"][2]
+    lv = bench.m2ae_levels(bench.CONFIGS["c3"])
+    assert [l[0] for l in lv] == [2048, 512, 256]            # level l+1 groups the G_l centres of level l
+    assert [l[3] for l in lv] == c3["M"] == [410, 205, 52]    # G - int(G * (1 - 0.8))
+    x, lps, preds = bench.m2ae_inputs((4,) + bench.CONFIGS["c3"][1:], 3)
+    assert x.shape == (4, 2048, 3) and [p.shape for p in preds] == [(4 * 410, 16, 3), (4 * 205, 8, 3), (4 * 52, 8, 3)]
+
+
+def test_reference_arm_prints_the_native_config(capsys):
+    """`bench.py --impl reference` (the CPU oracle arm) prints the same `config` dictionary as the native arm."""
+    import json
+    import types
+    import bench
+    cfg = (8,) + bench.CONFIGS["c2"][1:]
+    bench.run_reference(types.SimpleNamespace(steps=2, warmup=1, gpus=1), cfg)
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["config"] == bench.config_dict(cfg)
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0

@@ -1,5 +1,7 @@
 """CPU tests of the oracle itself: the C restatement against the independent NumPy restatement, and both
 against the golden vectors produced by the reference's own glue code (tests/golden/make_golden.py)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -248,6 +250,16 @@ def test_rand_mask_pin(golden):
     assert np.array_equal(no.rand_mask(ref.astype(np.float32), num_mask), ref.astype(np.uint8))
     assert np.array_equal(co.hard_mask(np.zeros_like(ref, dtype=np.float32), 64 - num_mask, 0, ref.astype(np.float32)),
                           ref.astype(np.uint8))
+
+
+def test_block_mask_pin():
+    """`_mask_center_block` restated in NumPy against the reference method's own output (reference_block_mask.npz,
+    tests/golden/make_golden_block_mask.py), with the reference's `random.randint` picks."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_block_mask.npz"))
+    for tag in g["cases"]:
+        m = no.mask_center_block(g[f"{tag}_centers"], float(g[f"{tag}_ratio"][0]), g[f"{tag}_picks"])
+        assert np.array_equal(m, g[f"{tag}_mask"]), tag
+        assert (m.sum(1) == int(float(g[f"{tag}_ratio"][0]) * m.shape[1])).all()
 
 
 def test_hard_mask_c_vs_numpy_with_ties():
