@@ -10,9 +10,10 @@ namespace gm3d {
 
 // ---- the step's {sum, sum_sq, count} across ranks, over peer memory (include/gm3d.h: gm3d_step_reduce_t) ----------
 // Called by every thread of the tail CTA; thread 0 holds this rank's values.  Thread r < world pushes them into rank
-// r's inbox (data, then the launch counter as a release flag, both system scope), then waits for rank r's
-// contribution in the local inbox; thread 0 sums in rank order.  One NVLink store latency + one flag round: ~2-4 us,
-// on one CTA, behind the last patch of the step -- under programmatic dependent launch the next step already runs.
+// r's inbox (16 bytes of data, then the slot's launch count as a release flag, both system scope).  defer = 1: that is
+// all -- gm3d_step_reduce_collect (step_reduce.cu) sums later, for a whole range of slots, and no loss launch ever
+// waits for another rank.  defer = 0: thread r then waits (bounded) for rank r's push of the same launch count in the
+// local inbox and thread 0 sums in rank order -- one NVLink store latency + one flag round, ~2-4 us on one CTA.
 struct InboxSlot {
     float sum, sq, cnt, pad;
     unsigned flag, pad2[3];
