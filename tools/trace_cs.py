@@ -26,7 +26,7 @@ from gm3d_b200.pipeline import GroupLossStep, StepRing  # noqa: E402
 
 steps = []
 for r in range(8):
-    s = GroupLossStep(B, N, G, k, ratio, device=dev, seed=1)
+    s = GroupLossStep(B, N, G, k, ratio, device=dev, seed=1, path="single")  # the trace lives in the one-launch kernel (-DGM3D_CS_DEBUG build)
     x, lp, pred = synthetic_batch(B, N, G, k, s.M, 1234 + r)
     s.xyz.copy_(torch.from_numpy(x)); s.loss_pred.copy_(torch.from_numpy(lp)); s.pred.copy_(torch.from_numpy(pred))
     steps.append(s)
