@@ -49,6 +49,7 @@ SIGNATURES = {
     "gm3d_chamfer_fused_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "gm3d_chamfer_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _i, _i, _i, _vp, _vp, _vp]),
     "gm3d_select_patches_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "gm3d_feature_mse_f32": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "gm3d_hard_mask_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _u64, _u64, _vp, _vp, _i, _vp]),
     "gm3d_loss_stats_f32": (_i, [_vp, _i, _vp, _vp]),
     "gm3d_learning_loss_f32": (_i, [_vp, _vp, _i, _i, _i, ctypes.c_float, _vp, _vp, _vp, _vp]),

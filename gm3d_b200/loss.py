@@ -83,6 +83,23 @@ class _FusedMaskedChamfer(torch.autograd.Function):
         return g, None, None, None
 
 
+class _FeatureMSE(torch.autograd.Function):
+    """Rows of the normalised-feature MSE (pred (R,D) vs pool[index]); gradient w.r.t. pred only (the reference
+    detaches the feature target).  One launch forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, pred, pool, index):
+        loss, _ = ops.feature_mse(pred, pool, index)
+        ctx.save_for_backward(pred, pool, index)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, pool, index = ctx.saved_tensors
+        _, grad = ops.feature_mse(pred, pool, index, gloss=g.contiguous().float(), want_loss=False, want_grad=True)
+        return grad, None, None
+
+
 def masked_patch_index(mask: torch.Tensor, num_masked: int) -> torch.Tensor:
     """(B,G) 0/1 mask (float, bool or uint8) -> (B*M,) int32 flat ids b*G+g of the masked patches, in order."""
     if mask.dtype not in (torch.bool, torch.uint8):
@@ -118,14 +135,12 @@ def forward_loss_feature(pred: torch.Tensor, target: torch.Tensor, mask: torch.T
     """Feature mode: normalised-feature MSE (N, M) + per-patch Chamfer (N, M)."""
     N, P_, D = target.shape
     bmask = mask if mask.dtype == torch.bool else mask != 0
-    tgt = target[bmask].reshape(N, -1, D)
-    PP = tgt.shape[1]
-    pred = torch.nn.functional.normalize(pred, p=2, dim=-1)
-    tgt = torch.nn.functional.normalize(tgt, p=2, dim=-1)
-    loss_mse = ((pred - tgt) ** 2).sum(dim=-1)
+    PP = pred.numel() // (N * D)
+    index = masked_patch_index(bmask, PP)  # serves both halves: `target[mask]` and `point_target[mask]`
+    loss_mse = _FeatureMSE.apply(pred.reshape(N * PP, D).to(dtype=torch.float32).contiguous(),
+                                 target.reshape(N * P_, D).to(dtype=torch.float32).contiguous(), index).reshape(N, PP)
 
     n = point_target.shape[2]
-    index = masked_patch_index(bmask, PP)
     rec = point_reconstructed.reshape(N * PP, -1, 3).to(dtype=torch.float32).contiguous()
     pool = point_target.reshape(N * P_, n, 3).to(dtype=torch.float32).contiguous()
     if per_point == "patch":

@@ -13,7 +13,7 @@ from . import _lib
 
 __all__ = [
     "furthest_point_sample", "fps_centers", "gather", "gather_grad", "knn", "group", "chamfer_forward",
-    "chamfer_fused", "chamfer_backward", "select_patches", "hard_mask", "loss_stats", "learning_loss",
+    "chamfer_fused", "chamfer_backward", "select_patches", "hard_mask", "feature_mse", "loss_stats", "learning_loss",
     "scale_translate_", "gather_points",
 ]
 
@@ -313,6 +313,33 @@ def hard_mask(loss_pred: Optional[torch.Tensor], B: int, L: int, len_keep: int, 
                                                 0, torch.cuda.current_stream(device).cuda_stream)
             _lib.check("gm3d_hard_mask_f32", rc)
     return (mask, index) if want_index else mask
+
+
+def feature_mse(pred: torch.Tensor, target: torch.Tensor, index: Optional[torch.Tensor] = None,
+                gloss: Optional[torch.Tensor] = None, want_loss: bool = True, want_grad: bool = False):
+    """Normalised-feature MSE rows (include/gm3d.h: gm3d_feature_mse_f32).  pred (R,D), target (T,D) f32, index (R) int32
+    or None -> (loss (R,) or None, grad (R,D) = gloss[:,None] * d loss / d pred or None)."""
+    _req(pred, "pred", torch.float32, 2)
+    _req(target, "target", torch.float32, 2)
+    R, D = pred.shape
+    if target.shape[1] != D:
+        raise ValueError("pred and target disagree on the feature dimension")
+    if index is not None:
+        _req(index, "index", torch.int32, 1)
+        if index.shape[0] != R:
+            raise ValueError("index must have one entry per pred row")
+    elif target.shape[0] != R:
+        raise ValueError("pred and target disagree on the number of rows")
+    if gloss is not None:
+        _req(gloss, "gloss", torch.float32, 1)
+    with torch.cuda.device(pred.device):
+        loss = torch.empty((R,), dtype=torch.float32, device=pred.device) if want_loss else None
+        grad = torch.empty((R, D), dtype=torch.float32, device=pred.device) if want_grad else None
+        if R > 0 and D > 0:
+            rc = _lib.load().gm3d_feature_mse_f32(_p(pred), _p(target), _p(index), R, D, _p(loss), _p(gloss), _p(grad),
+                                                  _stream(pred))
+            _lib.check("gm3d_feature_mse_f32", rc)
+    return loss, grad
 
 
 def loss_stats(per_patch: torch.Tensor) -> torch.Tensor:

@@ -21,6 +21,8 @@
  *   gm3d_chamfer_bwd_f32    chamfer.backward (ChamferFunction)      tools/runner_pretrain.py:138-151
  *   gm3d_select_patches_f32 `neighborhood[mask].reshape(B*M,-1,3)`  models/Point_MAE.py:425,
  *                                                                   ..._Classifier_SVM.py:972
+ *   gm3d_feature_mse_f32    forward_loss (feature mode): normalize, target[mask], squared difference, + backward
+ *                                                                   ..._feature_besed.py:979-985
  *   gm3d_hard_mask_f32      generate_mask / _mask_center_rand       ..._feature_besed.py:1062-1109,
  *                                                                   models/Point_MAE.py:297-320
  *   gm3d_loss_stats_f32     the scalars fed to misc.all_reduce_mean util/misc.py:345-353,
@@ -246,6 +248,14 @@ int gm3d_chamfer_bwd_f32(const float* xyz1, const float* xyz2, const int32_t* xy
 int gm3d_select_patches_f32(const float* nbhd, const uint8_t* mask, int B, int G, int row_floats, int M, int invert,
                             float* out /* or NULL */, int32_t* patch_index /* or NULL */,
                             int32_t* status /* or NULL */, void* stream);
+
+/* Normalised-feature MSE of forward_loss in feature mode (..._feature_besed.py:979-985), value and gradient:
+ *   loss[r]   = sum_d (pred[r,d] / max(|pred[r]|, 1e-12) - t[d] / max(|t|, 1e-12))^2,  t = target[index ? index[r] : r]
+ *   grad[r,:] = gloss[r] * d loss[r] / d pred[r,:]   (gloss == NULL: 1)
+ * pred (R,D), target (T,D) f32, index (R) int32 or NULL (the `target[mask]` select folded into the load).
+ * loss (R) and grad (R,D) may each be NULL, not both. */
+int gm3d_feature_mse_f32(const float* pred, const float* target, const int32_t* index /* or NULL */, int R, int D,
+                         float* loss /* or NULL */, const float* gloss /* or NULL */, float* grad /* or NULL */, void* stream);
 
 /* Hard-patch mask.  loss_pred (B,L) f32 -> mask (B,L) u8, 1 = masked, exactly L - len_keep ones per row:
  * the len_loss largest loss_pred (stable order: ties -> higher index is larger) plus the

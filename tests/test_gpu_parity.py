@@ -584,11 +584,19 @@ def test_forward_loss_matches_reference_golden(cuda, golden):
         want = d.min(2).values if mode == "dist1" else d.min(2).values + d.min(1).values
         want.mean().backward()
         assert (p.grad.reshape(-1, 32, 3).double() - p64.grad).abs().max() <= RTOL * p64.grad.abs().max()
-        r2 = loss.forward_loss_feature(dev(golden["loss_feature_pred"], cuda), dev(golden["loss_feature_target"], cuda),
-                                       mask, nb, pred, per_point=mode)
+        fp = dev(golden["loss_feature_pred"], cuda).clone().requires_grad_(True)
+        r2 = loss.forward_loss_feature(fp, dev(golden["loss_feature_target"], cuda), mask, nb, pred, per_point=mode)
         assert np.allclose(host(r2["matrix"]), golden[f"loss_feature_{mode}_matrix"], rtol=1e-4, atol=1e-6)
         assert np.isclose(r2["Chamfer_mean"].item(), golden[f"loss_feature_{mode}_chamfer_mean"], rtol=RTOL)
         assert np.isclose(r2["MSE_mean"].item(), golden[f"loss_feature_{mode}_mse_mean"], rtol=1e-5)
+        # gradient of the normalised-feature MSE (gm3d_feature_mse_f32) against float64 autograd of the reference lines
+        wgt = torch.rand(r2["matrix"].shape, device=cuda)
+        (r2["MSE_mean"] + (r2["matrix"].detach() * 0 + wgt * (r2["matrix"] - r2["matrix"].detach())).sum()).backward()
+        f64 = dev(golden["loss_feature_pred"], cuda).double().requires_grad_(True)
+        t64 = dev(golden["loss_feature_target"], cuda).double()[mask].reshape(f64.shape)
+        m64 = ((torch.nn.functional.normalize(f64, dim=-1) - torch.nn.functional.normalize(t64, dim=-1)) ** 2).sum(-1)
+        (m64.mean() + (wgt.double() * m64).sum()).backward()
+        assert (fp.grad.double() - f64.grad).abs().max() <= 1e-5 * f64.grad.abs().max()
     # stock scalar losses (models/Point_MAE.py:426)
     from gm3d_b200.chamfer import ChamferDistanceL1, ChamferDistanceL2
     gt = nb[mask].reshape(-1, 32, 3)
